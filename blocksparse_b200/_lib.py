@@ -1,0 +1,88 @@
+"""ctypes binding of csrc/libbsmm_b200.so (the C ABI declared in include/bsmm_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call
+fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbsmm_b200.so")
+
+F32, F16, BF16 = 0, 1, 2
+FLAG_FORCE_GENERIC, FLAG_FORCE_TC = 1, 2
+MAX_PAIRS = 8
+
+_c = ctypes
+_vp, _i, _f = _c.c_void_p, _c.c_int, _c.c_float
+
+# name -> (restype, argtypes); must list every symbol include/bsmm_b200.h declares
+SIGNATURES = {
+    "bsmm_version": (_i, []),
+    "bsmm_last_error": (_c.c_char_p, []),
+    "bsmm_last_kernel": (_c.c_char_p, []),
+    "bsmm_device_info": (_i, [_c.POINTER(_i)] * 3),
+    "bsmm_xprop": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "bsmm_updat": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i,
+                        _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _vp]),
+    "bsmm_gate_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "bst_nt": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "bst_xn": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "bst_softmax": (_i, [_i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "bst_softmax_grad": (_i, [_i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "bst_autoregressive_mask": (_i, [_i, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "bsmm_timer_create": (_i, [_c.POINTER(_vp)]),
+    "bsmm_timer_begin": (_i, [_vp, _vp]),
+    "bsmm_timer_end": (_i, [_vp, _vp, _c.POINTER(_f)]),
+    "bsmm_timer_destroy": (_i, [_vp]),
+}
+
+_lib = None
+
+
+class BsmmError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsmmError("%s not found: build it with `python __graft_entry__.py` or "
+                            "`make -C blocksparse_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is missing
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().bsmm_last_error().decode("utf-8", "replace")
+        if rc < 0:
+            raise ValueError("%s failed (%d): %s" % (what, rc, msg))
+        raise BsmmError("%s failed (cuda error %d): %s" % (what, rc, msg))
+
+
+def last_kernel():
+    return load().bsmm_last_kernel().decode()
+
+
+def dtype_code(torch_dtype):
+    import torch
+    try:
+        return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[torch_dtype]
+    except KeyError:
+        raise ValueError("unsupported dtype %s (float32, float16, bfloat16 only)" % (torch_dtype,))
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

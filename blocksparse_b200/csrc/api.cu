@@ -1,0 +1,310 @@
+// C ABI of libbsmm_b200.so -- argument validation and kernel-family dispatch.
+// See include/bsmm_b200.h for the contract and the reference launchers each entry replaces.
+#include "common.cuh"
+#include "generic.cuh"
+#include "softmax.cuh"
+#include "tc.cuh"
+
+using namespace bsmm;
+
+extern "C" {
+
+int bsmm_version(void) { return 1000 * 0 + 1; }
+const char* bsmm_last_error(void) { return err_buf(); }
+const char* bsmm_last_kernel(void) { return kernel_name_slot(); }
+
+int bsmm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  const DeviceInfo& d = device_info();
+  if (!d.ok) return fail(BSMM_E_NODEV, "no CUDA device");
+  if (sm_count) *sm_count = d.sm_count;
+  if (cc_major) *cc_major = d.cc_major;
+  if (cc_minor) *cc_minor = d.cc_minor;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+static int check_bsize_axis(int bsize, int axis) {
+  if (axis != 0 && axis != 1) return fail(BSMM_E_BSIZE, "feature axis must be 0 or 1, got %d", axis);
+  if (bsize != 8 && bsize != 16 && bsize != 32 && bsize != 64)
+    return fail(BSMM_E_BSIZE, "block size must be 8, 16, 32 or 64, got %d", bsize);
+  return 0;
+}
+
+int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
+               const int32_t* lut, int n_out, int n_in, int blocks,
+               const void* x, const void* w, void* y, int N,
+               const float* gate,
+               const int32_t* sched, int sched_len,
+               int flags, void* stream) {
+  if (int e = check_bsize_axis(bsize, axis)) return e;
+  if (!lut || !x || !w || !y) return fail(BSMM_E_ARG, "bsmm_xprop: null pointer");
+  if (n_out <= 0 || n_in <= 0 || blocks < 0 || N < 0) return fail(BSMM_E_ARG, "bsmm_xprop: bad sizes");
+  // reference limit: C, K < bsize*65536 (src/blocksparse_matmul_op.cc:96-97)
+  if (n_out >= 65536 || n_in >= 65536) return fail(BSMM_E_LIMIT, "bsmm_xprop: more than 65535 blocks per dimension");
+  if (N == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
+    int rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_len, s);
+    if (rc != TC_NOT_APPLICABLE) return rc;
+    if (flags & BSMM_FLAG_FORCE_TC)
+      return fail(BSMM_E_ARG, "bsmm_xprop: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());
+  } else if (flags & BSMM_FLAG_FORCE_TC) {
+    return fail(BSMM_E_ARG, "bsmm_xprop: contradictory flags");
+  }
+
+  XnParams p = {};
+  p.lut = lut; p.lut_head_stride = 0; p.n_out = n_out;
+  p.w = w; p.w_z_stride = 0;
+  p.x = x; p.y = y;
+  p.heads = 1; p.N = N; p.gate = gate;
+  if (axis == 0) { p.x_sf = N; p.x_sn = 1; p.y_sf = N; p.y_sn = 1; }
+  else { p.x_sf = 1; p.x_sn = (long long)n_in * bsize; p.y_sf = 1; p.y_sn = (long long)n_out * bsize; }
+  // Wm[fi][fo]: fprop uses W[fi][fo] directly, bprop needs the transpose.
+  const bool trans_w = bprop != 0;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    BSMM_DISPATCH_BSIZE(bsize, BS, { return launch_sdd_xn<T, T, BS>(p, axis == 1, trans_w, 1, s); });
+  });
+  return 0;
+}
+
+int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
+               const int32_t* updat_lut, int blocks, int n_c_blocks, int n_k_blocks,
+               const void* const* xs, const void* const* dys, int pcount,
+               void* dw, int N, float alpha, float beta,
+               const float* gate, int gated_dw,
+               const int32_t* sched, int sched_len,
+               int flags, void* stream) {
+  if (int e = check_bsize_axis(bsize, axis)) return e;
+  if (!updat_lut || !xs || !dys || !dw) return fail(BSMM_E_ARG, "bsmm_updat: null pointer");
+  if (pcount < 1 || pcount > BSMM_MAX_PAIRS)
+    return fail(BSMM_E_ARG, "bsmm_updat: pcount must be in [1,%d], got %d", BSMM_MAX_PAIRS, pcount);
+  if (beta != 0.f && beta != 1.f) return fail(BSMM_E_ARG, "bsmm_updat: beta must be 0 or 1");
+  if (dw_dtype != dtype && dw_dtype != BSMM_F32) return fail(BSMM_E_DTYPE, "bsmm_updat: dw dtype must be fp32 or the input dtype");
+  if (blocks <= 0 || N < 0) return fail(BSMM_E_ARG, "bsmm_updat: bad sizes");
+  for (int i = 0; i < pcount; ++i)
+    if (!xs[i] || !dys[i]) return fail(BSMM_E_ARG, "bsmm_updat: null pointer in pair %d", i);
+  cudaStream_t s = (cudaStream_t)stream;
+
+  if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
+    int rc = tc_updat(dtype, dw_dtype, axis, bsize, updat_lut, blocks, n_c_blocks, n_k_blocks, xs, dys, pcount,
+                      dw, N, alpha, beta, gate, gated_dw, sched, sched_len, s);
+    if (rc != TC_NOT_APPLICABLE) return rc;
+    if (flags & BSMM_FLAG_FORCE_TC)
+      return fail(BSMM_E_ARG, "bsmm_updat: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());
+  }
+
+  NtParams p = {};
+  p.lut = updat_lut; p.lut_head_stride = 0; p.blocks = blocks;
+  for (int i = 0; i < pcount; ++i) { p.a[i] = xs[i]; p.b[i] = dys[i]; }
+  p.pcount = pcount; p.out = dw; p.out_z_stride = 0;
+  p.R = N; p.heads = 1; p.alpha = alpha; p.beta = beta; p.gate = gate; p.gated = gated_dw && gate;
+  if (axis == 0) { p.a_sf = N; p.a_sr = 1; p.b_sf = N; p.b_sr = 1; }
+  else { p.a_sf = 1; p.a_sr = (long long)n_c_blocks * bsize; p.b_sf = 1; p.b_sr = (long long)n_k_blocks * bsize; }
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    BSMM_DISPATCH_BSIZE(bsize, BS, {
+      if (dw_dtype == BSMM_F32) return launch_dds_nt<T, float, BS>(p, axis == 1, 1, s);
+      else                      return launch_dds_nt<T, T, BS>(p, axis == 1, 1, s);
+    });
+  });
+  return 0;
+}
+
+int bsmm_gate_grad(int dtype, int bsize, int blocks, const void* dw, const void* w, float* dg, void* stream) {
+  if (!dw || !w || !dg || blocks <= 0) return fail(BSMM_E_ARG, "bsmm_gate_grad: bad arguments");
+  if (int e = check_bsize_axis(bsize, 0)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int warps = 4;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    gate_grad_kernel<T><<<(blocks + warps - 1) / warps, warps * 32, 0, s>>>(
+        (const T*)dw, (const T*)w, dg, blocks, bsize * bsize);
+  });
+  return check_launch("gate_grad");
+}
+
+// ---------------------------------------------------------------------------------------
+static int check_bst(int bsize, int lut_heads, int heads, int head_state, int batch, int blocks) {
+  if (bsize != 8 && bsize != 16 && bsize != 32 && bsize != 64)
+    return fail(BSMM_E_BSIZE, "block size must be 8, 16, 32 or 64, got %d", bsize);
+  if (lut_heads != 1 && lut_heads != heads) return fail(BSMM_E_ARG, "lut_heads must be 1 or heads");
+  if (batch <= 0 || heads <= 0 || blocks <= 0) return fail(BSMM_E_ARG, "bad batch/heads/blocks");
+  if (head_state <= 0 || (head_state & 7)) return fail(BSMM_E_ARG, "head_state must be a positive multiple of 8 (bst_op.cc:208)");
+  return 0;
+}
+
+int bst_nt(int dtype, int c_dtype, int bsize,
+           const int32_t* nt_lut, int lut_heads, int blocks,
+           const void* a, const void* b, void* c,
+           int batch, int heads, int head_state, int ctx_blks_a, int ctx_blks_b,
+           int flags, void* stream) {
+  if (int e = check_bst(bsize, lut_heads, heads, head_state, batch, blocks)) return e;
+  if (!nt_lut || !a || !b || !c) return fail(BSMM_E_ARG, "bst_nt: null pointer");
+  // attention tensor must have < 2^32 elements (bst_op.cc:214)
+  if ((unsigned long long)batch * heads * blocks * bsize * bsize >= (1ull << 32))
+    return fail(BSMM_E_LIMIT, "bst_nt: output has >= 2^32 elements");
+  cudaStream_t s = (cudaStream_t)stream;
+
+  if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
+    int rc = tc_bst_nt(dtype, c_dtype, bsize, nt_lut, lut_heads, blocks, a, b, c, batch, heads, head_state,
+                       ctx_blks_a, ctx_blks_b, s);
+    if (rc != TC_NOT_APPLICABLE) return rc;
+    if (flags & BSMM_FLAG_FORCE_TC) return fail(BSMM_E_ARG, "bst_nt: no tcgen05 kernel for this configuration (%s)", err_buf());
+  }
+
+  const long long S = (long long)heads * head_state;
+  NtParams p = {};
+  p.lut = nt_lut; p.lut_head_stride = lut_heads > 1 ? 2LL * blocks : 0; p.blocks = blocks;
+  p.a[0] = a; p.b[0] = b; p.pcount = 1; p.out = c;
+  p.a_zb = (long long)ctx_blks_a * bsize * S; p.a_zh = head_state;
+  p.b_zb = (long long)ctx_blks_b * bsize * S; p.b_zh = head_state;
+  p.a_sf = S; p.a_sr = 1; p.b_sf = S; p.b_sr = 1;
+  p.out_z_stride = (long long)blocks * bsize * bsize;
+  p.R = head_state; p.heads = heads; p.alpha = 1.f; p.beta = 0.f; p.gate = nullptr; p.gated = 0;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    BSMM_DISPATCH_DTYPE(c_dtype, TC, {
+      BSMM_DISPATCH_BSIZE(bsize, BS, { return launch_dds_nt<T, TC, BS>(p, false, batch * heads, s); });
+    });
+  });
+  return 0;
+}
+
+int bst_xn(int a_dtype, int dtype, int bsize, int transpose_a,
+           const int32_t* lut, int lut_heads, int blocks, int max_lut,
+           const void* a, const void* b, void* c,
+           int batch, int heads, int head_state, int ctx_blks_b, int ctx_blks_c,
+           int flags, void* stream) {
+  if (int e = check_bst(bsize, lut_heads, heads, head_state, batch, blocks)) return e;
+  if (!lut || !a || !b || !c) return fail(BSMM_E_ARG, "bst_xn: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+
+  if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
+    int rc = tc_bst_xn(a_dtype, dtype, bsize, transpose_a, lut, lut_heads, blocks, max_lut, a, b, c, batch, heads,
+                       head_state, ctx_blks_b, ctx_blks_c, s);
+    if (rc != TC_NOT_APPLICABLE) return rc;
+    if (flags & BSMM_FLAG_FORCE_TC) return fail(BSMM_E_ARG, "bst_xn: no tcgen05 kernel for this configuration (%s)", err_buf());
+  }
+
+  const long long S = (long long)heads * head_state;
+  XnParams p = {};
+  p.lut = lut; p.lut_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_c + blocks) : 0; p.n_out = ctx_blks_c;
+  p.w = a; p.w_z_stride = (long long)blocks * bsize * bsize;
+  p.x = b; p.y = c;
+  p.x_zb = (long long)ctx_blks_b * bsize * S; p.x_zh = head_state;
+  p.y_zb = (long long)ctx_blks_c * bsize * S; p.y_zh = head_state;
+  p.x_sf = S; p.x_sn = 1; p.y_sf = S; p.y_sn = 1;
+  p.N = head_state; p.heads = heads; p.gate = nullptr;
+  // NN: out row i of A (fo = i, fi = j) -> transposed staging; TN: fo = j, fi = i -> direct.
+  const bool trans_w = transpose_a == 0;
+  BSMM_DISPATCH_DTYPE(a_dtype, TA, {
+    BSMM_DISPATCH_DTYPE(dtype, T, {
+      BSMM_DISPATCH_BSIZE(bsize, BS, { return launch_sdd_xn<TA, T, BS>(p, false, trans_w, batch * heads, s); });
+    });
+  });
+  return 0;
+}
+
+int bst_softmax(int x_dtype, int y_dtype, int bsize,
+                const int32_t* nn_lut, const int32_t* nt_lut, int lut_heads, int blocks, int max_lut,
+                const void* mask, int mask_heads, int autoregress_at_key,
+                const void* x, void* y, float scale,
+                int batch, int heads, int ctx_blks_q, void* stream) {
+  if (int e = check_bst(bsize, lut_heads, heads, 8, batch, blocks)) return e;
+  if (!nn_lut || !x || !y) return fail(BSMM_E_ARG, "bst_softmax: null pointer");
+  if ((long long)max_lut * bsize > 32768) return fail(BSMM_E_LIMIT, "bst_softmax: max_lut*bsize > 32768 (bst_op.cc:383)");
+  if (autoregress_at_key >= 0 && (!mask || !nt_lut))
+    return fail(BSMM_E_ARG, "bst_softmax: autoregress_at_key needs a mask and nt_lut");
+  if (mask && mask_heads != 1 && mask_heads != heads) return fail(BSMM_E_ARG, "bst_softmax: mask_heads must be 1 or heads");
+  cudaStream_t s = (cudaStream_t)stream;
+  SoftmaxParams p = {};
+  p.nn_lut = nn_lut; p.nt_lut = nt_lut;
+  p.nn_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_q + blocks) : 0;
+  p.nt_head_stride = lut_heads > 1 ? 2LL * blocks : 0;
+  p.mask = mask; p.mask_head_stride = (mask && mask_heads > 1) ? (long long)blocks * bsize : 0;
+  p.autoregress_at_key = autoregress_at_key;
+  p.x = x; p.y = y; p.scale = scale;
+  p.batch = batch; p.heads = heads; p.blocks = blocks; p.ctx_blks_q = ctx_blks_q;
+  BSMM_DISPATCH_DTYPE(x_dtype, TX, {
+    BSMM_DISPATCH_DTYPE(y_dtype, TY, {
+      BSMM_DISPATCH_BSIZE(bsize, BS, {
+        const long long groups = (long long)ctx_blks_q * (BS / (64 / BS));
+        dim3 grid((unsigned)((groups + SOFTMAX_WARPS - 1) / SOFTMAX_WARPS), heads, batch);
+        bst_softmax_kernel<TX, TY, BS><<<grid, SOFTMAX_WARPS * 32, 0, s>>>(p);
+      });
+    });
+  });
+  return check_launch("bst_softmax");
+}
+
+int bst_softmax_grad(int dtype, int dx_dtype, int bsize,
+                     const int32_t* nn_lut, int lut_heads, int blocks, int max_lut,
+                     const void* dy, const void* y, void* dx, float scale,
+                     int batch, int heads, int ctx_blks_q, void* stream) {
+  if (int e = check_bst(bsize, lut_heads, heads, 8, batch, blocks)) return e;
+  if (!nn_lut || !dy || !y || !dx) return fail(BSMM_E_ARG, "bst_softmax_grad: null pointer");
+  if ((long long)max_lut * bsize > 32768) return fail(BSMM_E_LIMIT, "bst_softmax_grad: max_lut*bsize > 32768");
+  cudaStream_t s = (cudaStream_t)stream;
+  SoftmaxParams p = {};
+  p.nn_lut = nn_lut;
+  p.nn_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_q + blocks) : 0;
+  p.x = dy; p.y_in = y; p.y = dx; p.scale = scale;
+  p.batch = batch; p.heads = heads; p.blocks = blocks; p.ctx_blks_q = ctx_blks_q;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    BSMM_DISPATCH_DTYPE(dx_dtype, TD, {
+      BSMM_DISPATCH_BSIZE(bsize, BS, {
+        const long long groups = (long long)ctx_blks_q * (BS / (64 / BS));
+        dim3 grid((unsigned)((groups + SOFTMAX_WARPS - 1) / SOFTMAX_WARPS), heads, batch);
+        bst_softmax_grad_kernel<T, TD, BS><<<grid, SOFTMAX_WARPS * 32, 0, s>>>(p);
+      });
+    });
+  });
+  return check_launch("bst_softmax_grad");
+}
+
+int bst_autoregressive_mask(int bsize, const int32_t* nt_lut, int lut_heads, int blocks,
+                            const void* mask_in, void* mask_out, int autoregress_at_key, void* stream) {
+  if (!nt_lut || !mask_in || !mask_out || lut_heads <= 0 || blocks <= 0)
+    return fail(BSMM_E_ARG, "bst_autoregressive_mask: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((blocks * bsize + 127) / 128, lut_heads);
+  BSMM_DISPATCH_BSIZE(bsize, BS, {
+    bst_autoregressive_mask_kernel<BS><<<grid, 128, 0, s>>>(nt_lut, lut_heads > 1 ? 2LL * blocks : 0,
+                                                            mask_in, mask_out, blocks, autoregress_at_key);
+  });
+  return check_launch("bst_autoregressive_mask");
+}
+
+// ---------------------------------------------------------------------------------------
+struct Timer { cudaEvent_t start, stop; };
+
+int bsmm_timer_create(void** timer) {
+  if (!timer) return fail(BSMM_E_ARG, "null timer");
+  Timer* t = new Timer;
+  if (cudaEventCreate(&t->start) != cudaSuccess || cudaEventCreate(&t->stop) != cudaSuccess) {
+    delete t;
+    return fail(BSMM_E_NODEV, "cudaEventCreate failed");
+  }
+  *timer = t;
+  return 0;
+}
+int bsmm_timer_begin(void* timer, void* stream) {
+  if (!timer) return fail(BSMM_E_ARG, "null timer");
+  return (int)cudaEventRecord(((Timer*)timer)->start, (cudaStream_t)stream);
+}
+int bsmm_timer_end(void* timer, void* stream, float* ms_out) {
+  if (!timer || !ms_out) return fail(BSMM_E_ARG, "null timer");
+  Timer* t = (Timer*)timer;
+  cudaError_t e = cudaEventRecord(t->stop, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(t->stop);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(ms_out, t->start, t->stop);
+  if (e != cudaSuccess) return fail((int)e, "timer: %s", cudaGetErrorString(e));
+  return 0;
+}
+int bsmm_timer_destroy(void* timer) {
+  if (!timer) return 0;
+  Timer* t = (Timer*)timer;
+  cudaEventDestroy(t->start); cudaEventDestroy(t->stop);
+  delete t;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+"""Host-side lookup-table construction (vectorised NumPy, no Python loops over blocks).
+
+Mirrors what BlocksparseMatMul.__init__ / xprop_lut (reference blocksparse/matmul.py:82-270)
+and BlocksparseTransformer.__init__ / xn_lut / init_softmax_mask
+(reference blocksparse/transformer.py:61-181) compute, plus the schedules our own
+kernels consume.  The reference builds these with O(blocks) interpreter loops; here
+everything is sorting / cumsum so a 128x128 layout takes well under a millisecond.
+"""
+import numpy as np
+
+SEG_MAX = (1 << 63) - 1
+
+
+def ceil_div(x, y):
+    return -(-x // y)
+
+
+def z_order_2d(x, y):
+    """Morton code, x on even bits and y on odd bits (reference blocksparse/utils.py:95-103).
+
+    Accepts scalars or integer arrays.
+    """
+    x = np.asarray(x, dtype=np.uint64)
+    y = np.asarray(y, dtype=np.uint64)
+    code = np.zeros(np.broadcast(x, y).shape, dtype=np.uint64)
+    for bit in range(32):
+        b = np.uint64(bit)
+        code |= ((x >> b) & np.uint64(1)) << np.uint64(2 * bit)
+        code |= ((y >> b) & np.uint64(1)) << np.uint64(2 * bit + 1)
+    return code if code.shape else int(code)
+
+
+def _group(outs, n_out):
+    """counts[o] and starts[o] for an array already sorted by output index."""
+    counts = np.bincount(outs, minlength=n_out).astype(np.int64)
+    starts = np.concatenate(([0], np.cumsum(counts)[:-1]))
+    return counts, starts
+
+
+def row_lut(outs, ins, wids, n_out):
+    """Kernel wire format ("row LUT", include/bsmm_b200.h): int32 [n_out + nnz][2].
+
+    `outs/ins/wids` must already be sorted by output index.  Header row o holds
+    (first_entry_row, n_entries); entry rows hold (w_block, in_block).
+    """
+    nnz = len(outs)
+    counts, starts = _group(outs, n_out)
+    lut = np.empty((n_out + nnz, 2), dtype=np.int32)
+    lut[:n_out, 0] = n_out + starts
+    lut[:n_out, 1] = counts
+    lut[n_out:, 0] = wids
+    lut[n_out:, 1] = ins
+    return lut, int(counts.max()) if nnz else 0
+
+
+def segmented_lut(outs, ins, wids, n_out, max_seg, min_seg):
+    """The reference's Volta wire format (blocksparse/matmul.py:172-270), kept for API parity.
+
+    Returns (lut, shared_bytes, n_segments, n_locks).  Segment rule (:218): a group is
+    cut after every `max_seg` entries as long as at least `min_seg` entries remain.
+    """
+    nnz = len(outs)
+    counts, starts = _group(outs, n_out)
+    nonempty = np.nonzero(counts)[0]
+    empty = np.nonzero(counts == 0)[0]
+    n = counts[nonempty]
+    if max_seg >= SEG_MAX:
+        cuts = np.zeros_like(n)
+    else:
+        cuts = np.where(n >= min_seg, (n - min_seg) // max_seg, 0)
+    segs_per = cuts + 1
+    n_seg_ne = int(segs_per.sum())
+    # segment -> (group, index within group)
+    grp = np.repeat(np.arange(len(nonempty)), segs_per)
+    first_seg = np.concatenate(([0], np.cumsum(segs_per)[:-1]))
+    j = np.arange(n_seg_ne) - first_seg[grp]
+    is_last = j == cuts[grp]
+    seg_len = np.where(is_last, n[grp] - cuts[grp] * max_seg if max_seg < SEG_MAX else n[grp], max_seg).astype(np.int64)
+    seg_start = starts[nonempty][grp] + j * (max_seg if max_seg < SEG_MAX else 0)
+    # lock ids: 1-based, in order of ascending output index, only for split groups
+    split = segs_per > 1
+    lock_of_group = np.where(split, np.cumsum(split), 0)
+    n_locks = int(split.sum())
+
+    n_seg = n_seg_ne + len(empty)
+    lut = np.empty(4 * n_seg + 2 * nnz, dtype=np.int32)
+    hdr = lut[:4 * n_seg].reshape(n_seg, 4)
+    hdr[:n_seg_ne, 0] = (4 * n_seg) // 2 + seg_start          # offset in int2 units
+    hdr[:n_seg_ne, 1] = seg_len
+    hdr[:n_seg_ne, 2] = nonempty[grp]
+    hdr[:n_seg_ne, 3] = lock_of_group[grp]
+    hdr[n_seg_ne:, 0] = (4 * n_seg) // 2 + nnz
+    hdr[n_seg_ne:, 1] = 0
+    hdr[n_seg_ne:, 2] = empty
+    hdr[n_seg_ne:, 3] = 0
+    ent = lut[4 * n_seg:].reshape(nnz, 2)
+    ent[:, 0] = ins
+    ent[:, 1] = wids
+    longest = int(seg_len.max()) if n_seg_ne else 0
+    return lut, longest * 8, n_seg, n_locks
+
+
+def lists_from_sorted(outs, ins, wids, n_out):
+    """[(out, [(in, w), ...]), ...] in the reference's order: non-empty outputs ascending, then empty ones."""
+    counts, starts = _group(outs, n_out)
+    ins_l, w_l = ins.tolist(), wids.tolist()
+    res, tail = [], []
+    for o in range(n_out):
+        c, s = int(counts[o]), int(starts[o])
+        if c:
+            res.append((o, list(zip(ins_l[s:s + c], w_l[s:s + c]))))
+        else:
+            tail.append((o, []))
+    return res + tail
+
+
+class MatmulLuts(object):
+    """Everything BlocksparseMatMul derives from a 2-D layout."""
+
+    def __init__(self, layout, z_order=True):
+        lay = np.asarray(layout) != 0
+        assert lay.ndim == 2
+        CB, KB = lay.shape
+        self.CB, self.KB = CB, KB
+        col_sizes = lay.sum(axis=0)
+        if not col_sizes.any():
+            raise ValueError("layout has no non-zero blocks")
+        big = int(col_sizes.max())
+        small = int(col_sizes[col_sizes > 0].min())
+        # "assume symmetrical transpose": the same thresholds are used for bprop (matmul.py:94)
+        max_seg = max(ceil_div(big, 4), small * 2) if big / small > 2.0 else SEG_MAX
+        min_seg = max(ceil_div(max_seg, 4), 4)
+
+        # discovery order = column-major (k ascending, then c) -- the order the reference's
+        # comment at matmul.py:114 assumes scipy.sparse.find returns
+        ks, cs = np.nonzero(lay.T)
+        cs = cs.astype(np.int64)
+        ks = ks.astype(np.int64)
+        nnz = len(cs)
+        if z_order:
+            rank = np.argsort(z_order_2d(cs, ks), kind="stable")
+            wid = np.empty(nnz, dtype=np.int64)
+            wid[rank] = np.arange(nnz)
+            upd_c, upd_k = cs[rank], ks[rank]
+        else:
+            wid = np.arange(nnz, dtype=np.int64)
+            upd_c, upd_k = cs, ks
+        self.blocks = nnz
+        self.updat_lut = np.stack([upd_c, upd_k], axis=1).astype(np.int32)
+        self.updat_list = [tuple(r) for r in self.updat_lut.tolist()]
+
+        # fprop: grouped by k (already sorted); bprop: grouped by c (stable => k ascending inside)
+        by_c = np.argsort(cs, kind="stable")
+        f = (ks, cs, wid)
+        b = (cs[by_c], ks[by_c], wid[by_c])
+        self.fprop_lut, self.fprop_shared, self.fprop_segments, self.fprop_locks = \
+            segmented_lut(f[0], f[1], f[2], KB, max_seg, min_seg)
+        self.bprop_lut, self.bprop_shared, self.bprop_segments, self.bprop_locks = \
+            segmented_lut(b[0], b[1], b[2], CB, max_seg, min_seg)
+        self.fprop_list = lists_from_sorted(f[0], f[1], f[2], KB)
+        self.bprop_list = lists_from_sorted(b[0], b[1], b[2], CB)
+        self.fprop_rows, self.fprop_max = row_lut(f[0], f[1], f[2], KB)
+        self.bprop_rows, self.bprop_max = row_lut(b[0], b[1], b[2], CB)
+        self._f, self._b = f, b
+
+    def tile_schedule(self, bprop, blocks_per_tile):
+        outs, ins, wids = self._b if bprop else self._f
+        n_out = self.CB if bprop else self.KB
+        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile)
+
+
+def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile):
+    """Schedule for the tcgen05 xprop kernel (csrc/tc.cuh).
+
+    An output tile covers `blocks_per_tile` consecutive output blocks (their fp32
+    accumulators live side by side in tensor memory).  For every tile the schedule
+    lists each input block that feeds at least one of them ONCE, followed by the
+    (slot, w) pairs that consume it, so the kernel stages an activation tile a single
+    time and issues one MMA per pair against it.
+
+    int32 layout:
+      [0] n_tiles  [1] blocks_per_tile  [2] total groups  [3] total pairs
+      tile header   [n_tiles][4]  = (first_group, n_groups, first_out_block, n_out_blocks)
+      group records [groups ][4]  = (in_block, first_pair, n_pairs, 0)
+      pair records  [pairs  ][2]  = (slot_in_tile, w_block)
+    first_group / first_pair are absolute int32 offsets into the array.
+    """
+    T = int(blocks_per_tile)
+    n_tiles = ceil_div(n_out, T)
+    outs = np.asarray(outs, dtype=np.int64)
+    ins = np.asarray(ins, dtype=np.int64)
+    wids = np.asarray(wids, dtype=np.int64)
+    tile = outs // T
+    order = np.lexsort((outs, ins, tile))          # by tile, then input block, then slot
+    tile_s, ins_s, outs_s, w_s = tile[order], ins[order], outs[order], wids[order]
+    nnz = len(outs)
+    new_group = np.ones(nnz, dtype=bool)
+    if nnz:
+        new_group[1:] = (tile_s[1:] != tile_s[:-1]) | (ins_s[1:] != ins_s[:-1])
+    g_first = np.nonzero(new_group)[0]
+    n_groups = len(g_first)
+    g_count = np.diff(np.concatenate((g_first, [nnz])))
+    g_tile = tile_s[g_first]
+    groups_per_tile = np.bincount(g_tile, minlength=n_tiles)
+    tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
+
+    hdr_off = 4
+    grp_off = hdr_off + 4 * n_tiles
+    pair_off = grp_off + 4 * n_groups
+    sched = np.zeros(pair_off + 2 * nnz, dtype=np.int32)
+    sched[0:4] = (n_tiles, T, n_groups, nnz)
+    th = sched[hdr_off:grp_off].reshape(n_tiles, 4)
+    th[:, 0] = grp_off + 4 * tile_first_group
+    th[:, 1] = groups_per_tile
+    th[:, 2] = np.arange(n_tiles) * T
+    th[:, 3] = np.minimum(T, n_out - np.arange(n_tiles) * T)
+    gr = sched[grp_off:pair_off].reshape(n_groups, 4)
+    gr[:, 0] = ins_s[g_first]
+    gr[:, 1] = pair_off + 2 * g_first
+    gr[:, 2] = g_count
+    pr = sched[pair_off:].reshape(nnz, 2)
+    pr[:, 0] = outs_s - tile_s * T
+    pr[:, 1] = w_s
+    return sched
+
+
+# ---------------------------------------------------------------------------------------
+# block-sparse transformer
+# ---------------------------------------------------------------------------------------
+
+MASK_DTYPE = {8: np.uint8, 16: np.uint16, 32: np.uint32, 64: np.uint64}
+
+
+def xn_lut(outs, ins, n_out):
+    """reference transformer.py:161-181 for one head; block ids are positions in (q,k)-sorted order."""
+    nnz = len(outs)
+    bid = np.arange(nnz, dtype=np.int64)
+    order = np.argsort(outs, kind="stable")
+    lut, longest = row_lut(outs[order], ins[order], bid[order], n_out)
+    counts, starts = _group(outs[order], n_out)
+    b_l, i_l = bid[order].tolist(), ins[order].tolist()
+    rows = [list(zip(b_l[s:s + c], i_l[s:s + c])) for s, c in zip(starts.tolist(), counts.tolist())]
+    return lut, rows, longest
+
+
+class TransformerLuts(object):
+    """Everything BlocksparseTransformer derives from a (heads|1, q_blks, k_blks) layout."""
+
+    def __init__(self, layout, block_size, mask_callback=None):
+        lay = np.asarray(layout) != 0
+        assert lay.ndim == 3
+        self.lut_heads, self.ctx_blks_q, self.ctx_blks_k = lay.shape
+        self.blk_size = block_size
+        nt_luts, nn_luts, tn_luts = [], [], []
+        self.nt_list, self.nn_list, self.tn_list = [], [], []
+        self.nn_max = self.tn_max = 0
+        self.blocks = None
+        for h in range(self.lut_heads):
+            qs, ks = np.nonzero(lay[h])                # row-major == sorted by (q, k)
+            if self.blocks is None:
+                self.blocks = len(qs)
+            elif len(qs) != self.blocks:
+                raise ValueError("number of layout blocks must be equal across heads")
+            qs = qs.astype(np.int64)
+            ks = ks.astype(np.int64)
+            nn, nn_rows, nn_max = xn_lut(qs, ks, self.ctx_blks_q)
+            tn, tn_rows, tn_max = xn_lut(ks, qs, self.ctx_blks_k)
+            nt_luts.append(np.stack([qs, ks], axis=1).astype(np.int32))
+            nn_luts.append(nn)
+            tn_luts.append(tn)
+            self.nt_list.append(list(zip(qs.tolist(), ks.tolist())))
+            self.nn_list.append(nn_rows)
+            self.tn_list.append(tn_rows)
+            self.nn_max = max(self.nn_max, nn_max)
+            self.tn_max = max(self.tn_max, tn_max)
+        if not self.blocks:
+            raise ValueError("layout has no non-zero blocks")
+        self.nt_lut = np.stack(nt_luts)
+        self.nn_lut = np.stack(nn_luts)
+        self.tn_lut = np.stack(tn_luts)
+        self.softmax_mask = self.softmax_mask_np = None
+        if mask_callback is not None:
+            self.init_softmax_mask(mask_callback)
+
+    def init_softmax_mask(self, mask_callback):
+        """Bit j of word r of block b is set iff key j is visible to query r (transformer.py:135-159)."""
+        bs = self.blk_size
+        dt = MASK_DTYPE[bs]
+        weights = (np.uint64(1) << np.arange(bs, dtype=np.uint64))
+        masks = np.empty((self.lut_heads, self.blocks, bs), dtype=dt)
+        for h in range(self.lut_heads):
+            for b, (q, k) in enumerate(self.nt_list[h]):
+                m = np.asarray(mask_callback((bs, bs), h, q, k, b)).astype(bool)
+                if m.shape != (bs, bs):
+                    raise ValueError("mask_callback must return a (%d,%d) array" % (bs, bs))
+                masks[h, b] = (m.astype(np.uint64) * weights[None, :]).sum(axis=1, dtype=np.uint64).astype(dt)
+        self.softmax_mask_np = masks                                                     # heads, blocks, bs
+        self.softmax_mask = np.ascontiguousarray(masks.transpose(0, 2, 1))              # reference device layout

@@ -1,0 +1,337 @@
+"""BlocksparseMatMul for B200 -- host side.
+
+Keeps the Python op surface of the reference's blocksparse/matmul.py (class
+BlocksparseMatMul :74-483, gradient wiring :485-527, group_param_grads :612-731) but
+operates on torch tensors and calls the sm_100a kernels through the C ABI in
+include/bsmm_b200.h.  There is no CPU path: tensors must live on a CUDA device.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .lut import MatmulLuts
+
+# tcgen05 tile width (output blocks whose accumulators share one CTA's tensor memory)
+_TILE_BLOCKS = {32: 8, 64: 4}
+
+
+def _as_2d(t, axis, feat):
+    """Flatten all non-feature dims (reference op.cc:130-139)."""
+    if axis == 0:
+        if t.shape[0] != feat:
+            raise ValueError("expected feature dim %d on axis 0, got shape %s" % (feat, tuple(t.shape)))
+        return t.reshape(feat, -1)
+    if t.shape[-1] != feat:
+        raise ValueError("expected feature dim %d on the last axis, got shape %s" % (feat, tuple(t.shape)))
+    return t.reshape(-1, feat)
+
+
+class BlocksparseMatMul(object):
+    """Drop-in for blocksparse.matmul.BlocksparseMatMul (reference matmul.py:74).
+
+    layout        : 2-D 0/1 array (CB, KB) of active blocks
+    block_size    : 8, 16, 32 or 64 (any feature axis; the reference restricts the pairs, :84-89)
+    feature_axis  : 0 -> activations are (C, N);  1 -> activations are (N, C)
+    """
+
+    def __getstate__(self):
+        return (self.layout, self.bsize, self.axis, self.z_order, self.name)
+
+    def __setstate__(self, state):
+        self.__init__(*state)
+
+    def __init__(self, layout, block_size=32, feature_axis=0, z_order=True, name=None):
+        if feature_axis not in (0, 1) or block_size not in (8, 16, 32, 64):
+            raise ValueError("Unsupported block size with this feature axis")
+        layout = np.asarray(layout)
+        if layout.ndim != 2:
+            raise ValueError("layout must be 2-D")
+        self.axis, self.bsize = feature_axis, block_size
+        luts = MatmulLuts(layout, z_order=z_order)
+        self._luts = luts
+        for k in ("updat_list", "updat_lut", "fprop_list", "bprop_list", "fprop_lut", "bprop_lut",
+                  "fprop_shared", "bprop_shared", "fprop_segments", "bprop_segments",
+                  "fprop_locks", "bprop_locks", "blocks", "CB", "KB"):
+            setattr(self, k, getattr(luts, k))
+        self.z_order = z_order
+        self.name = name or "BlocksparseMatMul"
+        self.flops = self.blocks * block_size * block_size * 2
+        self.w_shape = (self.blocks, block_size, block_size)
+        self.g_shape = (self.blocks,)
+        self.count = 0
+        self.C, self.K = self.CB * block_size, self.KB * block_size
+        self.sparsity = round(float(self.blocks) / float(self.CB * self.KB), 3)
+        self.layout = layout != 0
+        self._dev = {}          # device -> dict of LUT tensors (uploaded once, matmul.py:33-53)
+
+    def i_shape(self, N):
+        return (N, self.C) if self.axis else (self.C, N)
+
+    def o_shape(self, N):
+        return (N, self.K) if self.axis else (self.K, N)
+
+    def block_coord(self, block):
+        return self.updat_list[block]
+
+    # ------------------------------------------------------------------ initialisers
+    def identity_init(self, scale=1.0, dtype=torch.float32, device="cuda"):
+        """W such that blocks on the (wrapped) diagonal are scale*I (matmul.py:317-329)."""
+        W = torch.zeros(self.w_shape, dtype=dtype, device=device)
+        cs, ks = self.updat_lut[:, 0], self.updat_lut[:, 1]
+        diag = np.nonzero((cs % self.KB) == (ks % self.CB))[0]
+        if len(diag):
+            W[torch.as_tensor(diag, device=device)] = scale * torch.eye(self.bsize, dtype=dtype, device=device)
+        return W
+
+    def checker_init(self, dtype=torch.float32, device="cuda"):
+        """Checkerboard gate (matmul.py:331-337)."""
+        cs, ks = self.updat_lut[:, 0], self.updat_lut[:, 1]
+        return torch.as_tensor(((cs & 1) ^ (ks & 1) ^ 1).astype(np.float32), device=device).to(dtype)
+
+    def prune(self, param, gate):
+        """Drop blocks whose gate is zero (matmul.py:272-291); returns (new_param, new_gate, new_layout)."""
+        gate_np = gate.detach().cpu().numpy() if torch.is_tensor(gate) else np.asarray(gate)
+        keep = gate_np != 0.0
+        layout = self.layout.copy()
+        for w in np.nonzero(~keep)[0]:
+            c, k = self.updat_list[w]
+            layout[c, k] = False
+        idx = torch.as_tensor(np.nonzero(keep)[0], device=param.device)
+        return param.index_select(0, idx), torch.ones(int(keep.sum()), dtype=gate.dtype, device=param.device), layout
+
+    # ------------------------------------------------------------------ device state
+    def _device_luts(self, device):
+        key = (device.type, device.index)
+        d = self._dev.get(key)
+        if d is None:
+            d = {
+                "fprop": torch.as_tensor(self._luts.fprop_rows, device=device),
+                "bprop": torch.as_tensor(self._luts.bprop_rows, device=device),
+                "updat": torch.as_tensor(self.updat_lut, device=device),
+            }
+            tb = _TILE_BLOCKS.get(self.bsize)
+            if tb:
+                d["fprop_sched"] = torch.as_tensor(self._luts.tile_schedule(False, tb), device=device)
+                d["bprop_sched"] = torch.as_tensor(self._luts.tile_schedule(True, tb), device=device)
+            self._dev[key] = d
+        return d
+
+    # ------------------------------------------------------------------ raw ops
+    def fprop(self, x, w, gate=None, flags=0):
+        return self._xprop(x, w, False, gate, flags)
+
+    def bprop(self, dy, w, gate=None, flags=0):
+        return self._xprop(dy, w, True, gate, flags)
+
+    def _xprop(self, x, w, bprop, gate, flags):
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.BsmmError("BlocksparseMatMul needs CUDA tensors (no CPU path)")
+        feat_in, feat_out = (self.K, self.C) if bprop else (self.C, self.K)
+        n_in, n_out = (self.KB, self.CB) if bprop else (self.CB, self.KB)
+        x2 = _as_2d(x, self.axis, feat_in).contiguous()
+        w = w.contiguous()
+        if tuple(w.shape) != self.w_shape:
+            raise ValueError("w must have shape %s, got %s" % (self.w_shape, tuple(w.shape)))
+        if w.dtype != x.dtype:
+            raise ValueError("x and w must have the same dtype")
+        N = x2.shape[1] if self.axis == 0 else x2.shape[0]
+        d = self._device_luts(x.device)
+        lut = d["bprop" if bprop else "fprop"]
+        sched = d.get("bprop_sched" if bprop else "fprop_sched")
+        y2 = torch.empty((feat_out, N) if self.axis == 0 else (N, feat_out), dtype=x.dtype, device=x.device)
+        if gate is not None:
+            gate = gate.to(torch.float32).contiguous()
+        rc = lib.bsmm_xprop(_lib.dtype_code(x.dtype), self.axis, self.bsize, int(bprop),
+                            lut.data_ptr(), n_out, n_in, self.blocks,
+                            x2.data_ptr(), w.data_ptr(), y2.data_ptr(), N,
+                            _lib.ptr(gate),
+                            _lib.ptr(sched), 0 if sched is None else sched.numel(),
+                            flags, _lib.stream_ptr())
+        _lib.check(rc, "bsmm_xprop")
+        if self.axis == 0:
+            return y2.reshape((feat_out,) + tuple(x.shape[1:]))
+        return y2.reshape(tuple(x.shape[:-1]) + (feat_out,))
+
+    def updat(self, xs, dys, dw=None, alpha=1.0, gate=None, dw_gated=False, dw_dtype=None, flags=0):
+        """DW[w] = alpha * sum_p X_p . DY_p^T (+ dw if given: in-place accumulate, DWA semantics)."""
+        lib = _lib.load()
+        if torch.is_tensor(xs):
+            xs, dys = [xs], [dys]
+        if len(xs) != len(dys) or not 1 <= len(xs) <= _lib.MAX_PAIRS:
+            raise ValueError("need 1..%d (x, dy) pairs" % _lib.MAX_PAIRS)
+        x0 = xs[0]
+        if not x0.is_cuda:
+            raise _lib.BsmmError("BlocksparseMatMul needs CUDA tensors (no CPU path)")
+        xs2 = [_as_2d(x, self.axis, self.C).contiguous() for x in xs]
+        dys2 = [_as_2d(e, self.axis, self.K).contiguous() for e in dys]
+        N = xs2[0].shape[1] if self.axis == 0 else xs2[0].shape[0]
+        for a, b in zip(xs2, dys2):
+            if a.dtype != x0.dtype or b.dtype != x0.dtype:
+                raise ValueError("all x / dy tensors must share one dtype")
+            if (a.shape[1] if self.axis == 0 else a.shape[0]) != N or (b.shape[1] if self.axis == 0 else b.shape[0]) != N:
+                raise ValueError("all x / dy tensors must share the minibatch size")
+        if dw is None:
+            out_dtype = dw_dtype or x0.dtype
+            dw = torch.empty(self.w_shape, dtype=out_dtype, device=x0.device)
+            beta = 0.0
+        else:
+            if tuple(dw.shape) != self.w_shape or not dw.is_contiguous():
+                raise ValueError("dw must be a contiguous tensor of shape %s" % (self.w_shape,))
+            beta = 1.0
+        if gate is not None:
+            gate = gate.to(torch.float32).contiguous()
+        arr_t = ctypes.c_void_p * len(xs2)
+        xp = arr_t(*[t.data_ptr() for t in xs2])
+        ep = arr_t(*[t.data_ptr() for t in dys2])
+        d = self._device_luts(x0.device)
+        rc = lib.bsmm_updat(_lib.dtype_code(x0.dtype), _lib.dtype_code(dw.dtype), self.axis, self.bsize,
+                            d["updat"].data_ptr(), self.blocks, self.CB, self.KB,
+                            xp, ep, len(xs2), dw.data_ptr(), N, float(alpha), beta,
+                            _lib.ptr(gate), int(bool(dw_gated)), None, 0, flags, _lib.stream_ptr())
+        _lib.check(rc, "bsmm_updat")
+        return dw
+
+    def gate_grad(self, dw, w):
+        """dg[w] = sum(dw[w] * w[w])  (BlocksparseMatmulDG, matmul.py:519-523)."""
+        lib = _lib.load()
+        dg = torch.empty(self.blocks, dtype=torch.float32, device=w.device)
+        dw = dw.to(w.dtype).contiguous()
+        rc = lib.bsmm_gate_grad(_lib.dtype_code(w.dtype), self.bsize, self.blocks, dw.data_ptr(),
+                                w.contiguous().data_ptr(), dg.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "bsmm_gate_grad")
+        return dg
+
+    # ------------------------------------------------------------------ autograd op
+    def matmul(self, I, W, gate=None, gate_grad=False, dw_gated=False, name=None, bench=0):
+        return self.__call__(I, W, gate=gate, gate_grad=gate_grad, dw_gated=dw_gated, name=name, bench=bench)
+
+    def __call__(self, I, W, gate=None, gate_grad=False, dw_gated=False, name=None, bench=0):
+        """y = bsmm(x, w) with gradients for x, w (and gate when gate_grad) -- matmul.py:458-527.
+
+        bench > 0 repeats the forward launch `bench` times between two CUDA events and prints
+        the reference's one-line report (op.cc:99-106, gpu_types.cc:43-87).
+        """
+        self.count += 1
+        if bench:
+            self._bench_forward(I, W, gate, bench, name or self.name)
+        return _BsmmFunction.apply(I, W, gate, self, bool(gate_grad), bool(dw_gated))
+
+    def _bench_forward(self, I, W, gate, repeat, name):
+        lib = _lib.load()
+        timer = ctypes.c_void_p()
+        _lib.check(lib.bsmm_timer_create(ctypes.byref(timer)), "timer_create")
+        self.fprop(I, W, gate)
+        _lib.check(lib.bsmm_timer_begin(timer, _lib.stream_ptr()), "timer_begin")
+        for _ in range(repeat):
+            self.fprop(I, W, gate)
+        ms = ctypes.c_float()
+        _lib.check(lib.bsmm_timer_end(timer, _lib.stream_ptr(), ctypes.byref(ms)), "timer_end")
+        lib.bsmm_timer_destroy(timer)
+        N = I.numel() // self.C
+        ms_per = ms.value / repeat
+        gflops = self.flops * N / (ms_per * 1e6)
+        print("%s fprop ms: %.4f gflops: %.0f" % (name, ms_per, gflops))
+        return ms_per
+
+
+class _BsmmFunction(torch.autograd.Function):
+    """Mirrors blocksparse_matmul_grad (reference matmul.py:485-527)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gate, bsmm, gate_grad, dw_gated):
+        ctx.bsmm, ctx.gate_grad, ctx.dw_gated = bsmm, gate_grad, dw_gated
+        ctx.save_for_backward(x, w, gate)
+        return bsmm.fprop(x, w, gate)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, gate = ctx.saved_tensors
+        bsmm = ctx.bsmm
+        dy = dy.contiguous()
+        dx = bsmm.bprop(dy, w, gate) if ctx.needs_input_grad[0] else None
+        dw = dg = None
+        want_dg = gate is not None and ctx.gate_grad and ctx.needs_input_grad[2]
+        if want_dg:
+            # reference matmul.py:519-523 + cn_64.cu:1340-1412: dw is produced ungated, then
+            # dg[w] = sum(dw[w] * w[w]) and dw is scaled by the gate in the same pass
+            raw = bsmm.updat([x], [dy])
+            dg = bsmm.gate_grad(raw, w).to(gate.dtype)
+            dw = raw * gate.to(raw.dtype).view(-1, 1, 1)
+        elif ctx.needs_input_grad[1]:
+            pending = _pending_group(bsmm, w)
+            if pending is not None:
+                dw = pending.add(x, dy, gate, ctx.dw_gated)
+            else:
+                dw = bsmm.updat([x], [dy], gate=gate, dw_gated=ctx.dw_gated)
+        return dx, dw, dg, None, None, None
+
+
+# ---------------------------------------------------------------------------------------
+# group_param_grads: fuse the dW of a weight that is reused T times into ceil(T/8) launches
+# (reference matmul.py:612-731 rewrites the TF graph; with eager autograd the same effect is
+# a context manager that defers the per-use updat calls and flushes them in groups).
+# ---------------------------------------------------------------------------------------
+
+_groups = {}
+
+
+class _Pending(object):
+    def __init__(self, bsmm, w, group_size):
+        self.bsmm, self.w, self.group_size = bsmm, w, group_size
+        self.xs, self.dys = [], []
+        self.gate, self.dw_gated = None, False
+        self.dw = None
+        self.launches = 0
+
+    def add(self, x, dy, gate, dw_gated):
+        self.xs.append(x)
+        self.dys.append(dy)
+        self.gate, self.dw_gated = gate, dw_gated
+        if len(self.xs) == self.group_size:
+            self.flush()
+        # autograd accumulates whatever backward returns into w.grad; the real sum is
+        # delivered once by finish(), so intermediate uses contribute nothing.
+        return None
+
+    def flush(self):
+        if not self.xs:
+            return
+        self.dw = self.bsmm.updat(self.xs, self.dys, dw=self.dw, gate=self.gate, dw_gated=self.dw_gated)
+        self.launches += 1
+        self.xs, self.dys = [], []
+
+
+def _pending_group(bsmm, w):
+    return _groups.get((id(bsmm), w.data_ptr()))
+
+
+class group_param_grads(object):
+    """with group_param_grads(bsmm, w, group_size=8): loss.backward()
+
+    Inside the block every backward use of `w` through `bsmm` hands its (x, dy) pair to
+    a pending list instead of launching its own updat; every `group_size` (<= 8) pairs
+    are flushed as ONE multi-pair launch that accumulates in place (DW then DWA in the
+    reference, matmul.py:681-692).  On exit the total is added to w.grad.
+    """
+
+    def __init__(self, bsmm, w, group_size=8):
+        assert 1 <= group_size <= _lib.MAX_PAIRS
+        self.key = (id(bsmm), w.data_ptr())
+        self.pending = _Pending(bsmm, w, group_size)
+        self.w = w
+
+    def __enter__(self):
+        _groups[self.key] = self.pending
+        return self.pending
+
+    def __exit__(self, *exc):
+        _groups.pop(self.key, None)
+        if exc[0] is None:
+            self.pending.flush()
+            if self.pending.dw is not None:
+                g = self.pending.dw.to(self.w.dtype)
+                self.w.grad = g if self.w.grad is None else self.w.grad + g
+        return False

@@ -1,0 +1,184 @@
+/*
+ * bsmm_b200.h -- C ABI of libbsmm_b200.so: block-sparse matmul (fprop / bprop / updat)
+ * and block-sparse transformer ops (NT / NN / TN, masked softmax, softmax grad,
+ * partial autoregressive mask) for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of openai/blocksparse.  Each entry
+ * point replaces one host launcher that the reference's TensorFlow OpKernels call
+ * (file:line relative to the reference tree):
+ *
+ *   bsmm_xprop            <- hgemm_blocksparse_xn_{64,128}_sdd / hgemm_blocksparse_nx_dsd /
+ *                            BsmmXprop_CN   (src/blocksparse_matmul_op.cc:49-68,185-215)
+ *   bsmm_updat            <- hgemm_blocksparse_nt_{64,128}_dds / hgemm_blocksparse_tn_dds /
+ *                            BsmmUpdat_CN   (src/blocksparse_matmul_op.cc:223-311)
+ *   bsmm_gate_grad        <- BlocksparseGateGrad (src/blocksparse_matmul_op.cc:490-540)
+ *   bst_nt                <- bst_hgemm_nt / bst_sgemm_nt   (src/bst_op.cc:139-144,183-250)
+ *   bst_xn                <- bst_hgemm_xn / bst_sgemm_xn   (src/bst_op.cc:251-320)
+ *   bst_softmax           <- BlocksparseMaskedSoftmax<T,V> (src/bst_op.cc:331-340,374-428)
+ *   bst_softmax_grad      <- BlocksparseSoftmaxGrad<T,V>   (src/bst_op.cc:443-512)
+ *   bst_autoregressive_mask <- BstPartialAutoregressiveMask (src/bst_op.cc:519-575)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer except `err` strings is DEVICE memory
+ *     owned by the caller (the library never allocates device memory and keeps no state
+ *     other than a lazily filled device-property cache);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     and performs no host synchronisation;
+ *   - return value 0 = success; >0 = cudaError_t from the launch; <0 = argument error
+ *     (BSMM_E_*).  bsmm_last_error() gives a thread-local message for the last failure;
+ *   - dtype codes: BSMM_F32 / BSMM_F16 / BSMM_BF16.  fp32 paths use true fp32 FMA (no TF32).
+ *
+ * LUT wire format consumed by xprop / xn / softmax ("row LUT", int32 [n_out + nnz][2]):
+ *   rows [0, n_out)        = (first_entry_row, n_entries)   one header per output block
+ *   rows [n_out, n_out+nnz) = (w_block, in_block)            grouped by output block
+ *   -- this IS the reference's bst nn_lut/tn_lut format (blocksparse/transformer.py:161-181);
+ *   the bsmm host layer emits the same format from fprop_list / bprop_list
+ *   (blocksparse/matmul.py:137-138) instead of the segmented/locked Volta format.
+ * updat / NT consume the reference's own updat_lut / nt_lut: int32 [blocks][2] = (c,k) / (q,k)
+ *   (blocksparse/matmul.py:134-135, transformer.py:107-111).
+ */
+#ifndef BSMM_B200_H_
+#define BSMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BSMM_F32 = 0, BSMM_F16 = 1, BSMM_BF16 = 2 };
+
+enum {
+  BSMM_E_DTYPE   = -1,   /* unsupported dtype (combination)            */
+  BSMM_E_BSIZE   = -2,   /* unsupported block size / axis combination  */
+  BSMM_E_ARG     = -3,   /* null pointer, negative size, pcount > 8 …  */
+  BSMM_E_LIMIT   = -4,   /* size limit exceeded (mirrors reference OP_REQUIRES) */
+  BSMM_E_NODEV   = -5,   /* no sm_100 device / driver entry point missing */
+  BSMM_E_ALIGN   = -6    /* pointer or leading dimension not aligned as the tensor-core path needs */
+};
+
+/* flags for bsmm_xprop / bsmm_updat / bst_* */
+enum {
+  BSMM_FLAG_FORCE_GENERIC = 1,   /* use the CUDA-core kernels even where a tcgen05 kernel exists */
+  BSMM_FLAG_FORCE_TC      = 2    /* fail (BSMM_E_ARG) instead of falling back to CUDA-core kernels */
+};
+
+#define BSMM_MAX_PAIRS 8         /* reference: <= 8 (x,dy) pairs per updat launch (op.cc:233-234) */
+
+/* ---- library / device ------------------------------------------------------------ */
+int         bsmm_version(void);                 /* 1000*major + minor */
+const char* bsmm_last_error(void);              /* thread-local, never NULL */
+int         bsmm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* name of the kernel family the last successful call on this thread dispatched to
+ * ("tcgen05_xprop_bs32", "fma_xprop", ...) -- used by tests to prove which path ran */
+const char* bsmm_last_kernel(void);
+
+/* ---- block-sparse matmul -------------------------------------------------------- */
+
+/*
+ * fprop (bprop=0):  axis 0: Y[k-blk,:,n] = sum_{(c,w) in lut[k]} W[w]^T X[c-blk,:,n] (*gate[w])
+ *                   axis 1: Y[n,k-blk]   = sum X[n,c-blk] W[w]
+ * bprop (bprop=1):  axis 0: DX[c-blk]    = sum_{(k,w) in lut[c]} W[w] DY[k-blk]
+ *                   axis 1: DX[n,c-blk]  = sum DY[n,k-blk] W[w]^T
+ * x: (n_in*bsize, N) for axis 0, (N, n_in*bsize) for axis 1; y likewise with n_out.
+ * w: (blocks, bsize, bsize), element [w][i][j], i = input-feature, j = output-feature of FPROP
+ *    (blocksparse/matmul.py:360,369).
+ * lut: row LUT grouped by output block (n_out headers).  Output blocks with no entries are
+ *    zero-filled (reference behaviour, cn_64.cu:243-253).
+ * sched: optional tile schedule for the tcgen05 kernels built by the host layer
+ *    (blocksparse_b200/lut.py:build_tile_schedule); NULL selects the CUDA-core kernels.
+ * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).
+ */
+int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
+               const int32_t* lut, int n_out, int n_in, int blocks,
+               const void* x, const void* w, void* y, int N,
+               const float* gate,
+               const int32_t* sched, int sched_len,
+               int flags, void* stream);
+
+/*
+ * updat:  DW[w] = alpha * sum_{p<pcount} X_p[c-blk] . DY_p[k-blk]^T  (+ beta * DW[w]),  (c,k) = updat_lut[w]
+ *   axis 0: X_p (C,N), DY_p (K,N);  axis 1: X_p (N,C), DY_p (N,K).
+ * xs/dys: HOST arrays of pcount device pointers (the reference passes them by value in
+ *   Plist<T,8>, gpu_types.h:167-170).  beta must be 0 or 1 (DWA accumulate-in-place, op.cc:262-272).
+ * dw_dtype: BSMM_F32 or `dtype` (the reference always produces the activation dtype; fp32
+ *   accumulation across launches is our extension).
+ * gate != NULL with gated_dw: blocks whose gate is 0 produce 0, others are scaled by the gate
+ *   (blocksparse/matmul.py:414-417).
+ */
+int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
+               const int32_t* updat_lut, int blocks, int n_c_blocks, int n_k_blocks,
+               const void* const* xs, const void* const* dys, int pcount,
+               void* dw, int N, float alpha, float beta,
+               const float* gate, int gated_dw,
+               const int32_t* sched, int sched_len,
+               int flags, void* stream);
+
+/* dg[w] = sum_ij dw[w][i][j] * w[w][i][j]   (BlocksparseMatmulDG, op.cc:490-540) */
+int bsmm_gate_grad(int dtype, int bsize, int blocks, const void* dw, const void* w,
+                   float* dg, void* stream);
+
+/* ---- block-sparse transformer ------------------------------------------------------ */
+
+/*
+ * NT: C[b,h,blk,:,:] = A[b, q-blk, h, :] . B[b, k-blk, h, :]^T     (q,k) = nt_lut[hl][blk]
+ *   a: (batch, ctx_blks_a*bsize, heads*head_state), b: (batch, ctx_blks_b*bsize, heads*head_state)
+ *   c: (batch, heads, blocks, bsize, bsize) of c_dtype.
+ *   nt_lut: int32 [lut_heads][blocks][2]; lut_heads in {1, heads}.
+ */
+int bst_nt(int dtype, int c_dtype, int bsize,
+           const int32_t* nt_lut, int lut_heads, int blocks,
+           const void* a, const void* b, void* c,
+           int batch, int heads, int head_state, int ctx_blks_a, int ctx_blks_b,
+           int flags, void* stream);
+
+/*
+ * XN: transpose_a=0 (NN): C[b, q-blk, h, :] = sum_{(blk,k) in lut[q]} A[b,h,blk]   . B[b, k-blk, h, :]
+ *     transpose_a=1 (TN): C[b, k-blk, h, :] = sum_{(blk,q) in lut[k]} A[b,h,blk]^T . B[b, q-blk, h, :]
+ *   lut: int32 [lut_heads][ctx_blks_c + blocks][2] -- the reference's nn_lut / tn_lut verbatim.
+ */
+int bst_xn(int a_dtype, int dtype, int bsize, int transpose_a,
+           const int32_t* lut, int lut_heads, int blocks, int max_lut,
+           const void* a, const void* b, void* c,
+           int batch, int heads, int head_state, int ctx_blks_b, int ctx_blks_c,
+           int flags, void* stream);
+
+/*
+ * y = softmax(scale * x) along each query row across all key blocks of the row, with an
+ * optional bit mask (bit j of word r of block blk set <=> key j visible to query r).
+ *   x, y: (batch, heads, blocks, bsize, bsize);  lut = nn_lut (rows = query blocks).
+ *   mask: NULL or uint{bsize}[mask_heads][blocks][bsize]  (the host layer's softmax_mask_np
+ *         layout, blocksparse/transformer.py:155) ; mask_heads in {1, heads}.
+ *   autoregress_at_key >= 0 applies the partial-autoregressive rewrite on the fly
+ *         (blocksparse/transformer.py:264-274); nt_lut is then required.
+ * Limit: max_lut * bsize <= 32768 (bst_op.cc:383).
+ */
+int bst_softmax(int x_dtype, int y_dtype, int bsize,
+                const int32_t* nn_lut, const int32_t* nt_lut, int lut_heads, int blocks, int max_lut,
+                const void* mask, int mask_heads, int autoregress_at_key,
+                const void* x, void* y, float scale,
+                int batch, int heads, int ctx_blks_q, void* stream);
+
+/* dx = (dy - sum_row(dy*y)) * y * scale   (blocksparse/transformer.py:301) */
+int bst_softmax_grad(int dtype, int dx_dtype, int bsize,
+                     const int32_t* nn_lut, int lut_heads, int blocks, int max_lut,
+                     const void* dy, const void* y, void* dx, float scale,
+                     int batch, int heads, int ctx_blks_q, void* stream);
+
+/* mask_out[hl][blk][r] = mask_in[hl][blk][r] & (ones >> shift(r)), same layout as bst_softmax's mask */
+int bst_autoregressive_mask(int bsize, const int32_t* nt_lut, int lut_heads, int blocks,
+                            const void* mask_in, void* mask_out, int autoregress_at_key,
+                            void* stream);
+
+/* ---- measurement helper (the reference's `bench` op attribute, op.cc:99-106) ---------
+ * Records two events around whatever the caller enqueues between begin and end.      */
+int bsmm_timer_create(void** timer);
+int bsmm_timer_begin(void* timer, void* stream);
+int bsmm_timer_end(void* timer, void* stream, float* ms_out);   /* synchronises on the stop event */
+int bsmm_timer_destroy(void* timer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSMM_B200_H_ */

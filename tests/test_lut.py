@@ -1,0 +1,143 @@
+"""Host logic (blocksparse_b200/lut.py) against the reference-generated fixtures and the oracle.
+
+The product LUT builder is vectorised NumPy and shares no code with oracle/; both
+must reproduce the reference's wire formats bit for bit.
+"""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from tests._util import GOLDEN, golden_files
+from tests.golden.make_golden import causal_callback, checker_callback
+from blocksparse_b200.lut import MatmulLuts, TransformerLuts, build_tile_schedule, z_order_2d
+from oracle.bsmm_oracle import MatmulOracle, z_order_2d as z_ref
+from oracle.bst_oracle import TransformerOracle
+
+
+def test_z_order_vectorised_matches_scalar():
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 70000, 200)
+    y = rng.integers(0, 70000, 200)
+    got = z_order_2d(x, y)
+    want = [z_ref(int(a), int(b)) for a, b in zip(x, y)]
+    assert got.tolist() == want
+    assert z_order_2d(3, 5) == z_ref(3, 5)
+
+
+@pytest.mark.parametrize("fname", golden_files("bsmm_"))
+def test_matmul_luts_match_reference(fname):
+    g = np.load(os.path.join(GOLDEN, fname))
+    L = MatmulLuts(g["layout"])
+    np.testing.assert_array_equal(L.fprop_lut, g["fprop_lut"])
+    np.testing.assert_array_equal(L.bprop_lut, g["bprop_lut"])
+    np.testing.assert_array_equal(L.updat_lut, g["updat_lut"])
+    meta = [L.fprop_segments, L.fprop_locks, L.fprop_shared, L.bprop_segments, L.bprop_locks, L.bprop_shared, L.blocks]
+    np.testing.assert_array_equal(np.array(meta), g["meta"][:7])
+
+
+def _random_layouts():
+    rng = np.random.default_rng(7)
+    for shape, d in [((1, 1), 1.0), ((3, 17), 0.3), ((40, 40), 0.05), ((33, 9), 0.6), ((64, 64), 0.2), ((128, 128), 0.1)]:
+        lay = (rng.random(shape) < d).astype(np.int32)
+        lay[rng.integers(shape[0]), rng.integers(shape[1])] = 1
+        yield lay
+    lay = (rng.random((48, 48)) < 0.04).astype(np.int32)
+    lay[:, :3] = 1          # skewed columns -> segmentation + locks
+    yield lay
+
+
+@pytest.mark.parametrize("z", [True, False])
+def test_matmul_luts_match_oracle_on_random_layouts(z):
+    for lay in _random_layouts():
+        L = MatmulLuts(lay, z_order=z)
+        O = MatmulOracle(lay, 32, 1, z_order=z)
+        np.testing.assert_array_equal(L.fprop_lut, O.fprop_lut)
+        np.testing.assert_array_equal(L.bprop_lut, O.bprop_lut)
+        np.testing.assert_array_equal(L.updat_lut, O.updat_lut)
+        assert (L.fprop_segments, L.fprop_locks, L.fprop_shared) == (O.fprop_segments, O.fprop_locks, O.fprop_shared)
+        assert (L.bprop_segments, L.bprop_locks, L.bprop_shared) == (O.bprop_segments, O.bprop_locks, O.bprop_shared)
+        assert L.fprop_list == O.fprop_list
+        assert L.bprop_list == O.bprop_list
+        assert L.updat_list == O.updat_list
+
+
+def _decode_rows(rows, n_out):
+    out = []
+    for o in range(n_out):
+        first, cnt = rows[o]
+        out.append([(int(rows[first + e][1]), int(rows[first + e][0])) for e in range(cnt)])   # (in, w)
+    return out
+
+
+def test_row_lut_and_tile_schedule_cover_every_block_once():
+    for lay in _random_layouts():
+        L = MatmulLuts(lay)
+        for bprop in (False, True):
+            rows = L.bprop_rows if bprop else L.fprop_rows
+            lists = dict(L.bprop_list if bprop else L.fprop_list)
+            n_out = L.CB if bprop else L.KB
+            dec = _decode_rows(rows, n_out)
+            for o in range(n_out):
+                assert dec[o] == lists[o]
+            for T in (4, 8, 16):
+                s = L.tile_schedule(bprop, T)
+                n_tiles, Tt, n_groups, n_pairs = s[:4]
+                assert Tt == T and n_pairs == L.blocks and n_tiles == -(-n_out // T)
+                seen = set()
+                for t in range(n_tiles):
+                    fg, ng, fo, no = s[4 + 4 * t: 8 + 4 * t]
+                    assert fo == t * T and no == min(T, n_out - fo)
+                    prev_in = -1
+                    for gi in range(ng):
+                        ib, fp, npair, _ = s[fg + 4 * gi: fg + 4 * gi + 4]
+                        assert ib > prev_in and npair >= 1
+                        prev_in = ib
+                        for pi in range(npair):
+                            slot, w = s[fp + 2 * pi: fp + 2 * pi + 2]
+                            assert 0 <= slot < no
+                            assert (int(ib), int(w)) in lists[fo + slot]
+                            seen.add(int(w))
+                assert len(seen) == L.blocks
+
+
+def _cb(name, has_mask):
+    if not has_mask:
+        return None
+    return checker_callback if "perhead" in name else causal_callback
+
+
+@pytest.mark.parametrize("fname", golden_files("bst_"))
+def test_transformer_luts_match_reference(fname):
+    g = np.load(os.path.join(GOLDEN, fname))
+    lay = g["layout"]
+    if lay.ndim == 2:
+        lay = lay[None]
+    L = TransformerLuts(lay, int(g["bs"]), _cb(fname, bool(g["has_mask"])))
+    np.testing.assert_array_equal(L.nt_lut, g["nt_lut"])
+    np.testing.assert_array_equal(L.nn_lut, g["nn_lut"])
+    np.testing.assert_array_equal(L.tn_lut, g["tn_lut"])
+    np.testing.assert_array_equal(np.array([L.blocks, L.nn_max, L.tn_max, L.ctx_blks_q, L.ctx_blks_k]), g["meta"])
+    if bool(g["has_mask"]):
+        np.testing.assert_array_equal(L.softmax_mask_np, g["mask_np"])
+        np.testing.assert_array_equal(L.softmax_mask, g["mask_dev"])
+    O = TransformerOracle(g["layout"], int(g["bs"]), heads=int(g["heads"]))
+    assert L.nt_list == O.nt_list and L.nn_list == O.nn_list and L.tn_list == O.tn_list
+
+
+def test_classes_construct_and_pickle_without_gpu():
+    from blocksparse_b200 import BlocksparseMatMul, BlocksparseTransformer
+    lay = np.eye(4, dtype=np.int32)
+    lay[0, 3] = 1
+    m = BlocksparseMatMul(lay, block_size=32, feature_axis=1)
+    assert m.w_shape == (5, 32, 32) and m.i_shape(7) == (7, 128) and m.o_shape(7) == (7, 128)
+    assert m.block_coord(0) == (0, 0) and m.flops == 5 * 32 * 32 * 2 and m.sparsity == round(5 / 16, 3)
+    m2 = pickle.loads(pickle.dumps(m))
+    np.testing.assert_array_equal(m2.fprop_lut, m.fprop_lut)
+    with pytest.raises(ValueError):
+        BlocksparseMatMul(lay, block_size=12)
+    t = BlocksparseTransformer(np.tril(np.ones((3, 3), np.int32)), block_size=16, heads=2, mask_callback=causal_callback)
+    assert t.blocks == 6 and t.nn_max == 3 and t.block_coord(1) == (1, 0)
+    t2 = pickle.loads(pickle.dumps(t))
+    np.testing.assert_array_equal(t2.softmax_mask_np, t.softmax_mask_np)
