@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the block-sparse matmul hot path on B200.
+
+A "step" = one fprop + one bprop + one updat of BlocksparseMatMul over one synthetic
+minibatch (BASELINE.json configs[1]: 4096x4096, block_size 32, bf16, N=4096 per GPU,
+density 25 % unless --density is given).  Metric = effective TFLOP/s
+= 3 * 2*nnz_blocks*bs^2*N / t  (the reference's own flop accounting, op.cc:102,182).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N>1 is launched by torchrun (one rank per GPU): the minibatch axis is sharded (weak
+scaling: every rank holds N=4096 columns), fprop/bprop need no communication and the
+updat output dW is all-reduced with NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C = K = 4096
+BS = 32
+N_PER_GPU = 4096
+SEED = 1236
+
+
+def make_layout(density, cb=C // BS, kb=K // BS, seed=SEED):
+    rng = np.random.default_rng(seed)
+    lay = (rng.random((cb, kb)) < density).astype(np.int32)
+    np.fill_diagonal(lay, 1)
+    return lay
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference(density, axis, budget_s=20.0, steps=1):
+    """The reference's path on the host cores: its NumPy checker math (blocksparse/matmul.py:353-419),
+    restated BLAS-batched in oracle/bsmm_oracle.py, on a bounded column sample of the same workload."""
+    from oracle.bsmm_oracle import MatmulOracle, fprop_fast, bprop_fast, updat_fast
+    lay = make_layout(density)
+    orc = MatmulOracle(lay, BS, axis)
+    rng = np.random.default_rng(SEED)
+    n = 1024                                 # columns of the 4096-wide minibatch timed per step
+    W = rng.normal(0, 0.01, orc.w_shape).astype(np.float32)
+    X = rng.normal(0, 0.1, orc.i_shape(n)).astype(np.float32)
+    E = rng.normal(0, 0.1, orc.o_shape(n)).astype(np.float32)
+    fprop_fast(orc, X[:8] if axis else X[:, :8], W)       # warm BLAS
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps or (time.perf_counter() - t0 < budget_s and done < 3):
+        fprop_fast(orc, X, W)
+        bprop_fast(orc, E, W)
+        updat_fast(orc, X, E)
+        done += 1
+    dt = (time.perf_counter() - t0) / done
+    flops = 3 * 2.0 * orc.blocks * BS * BS * n
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": int(threads), "kind": "port",
+            "sample": "fprop+bprop+updat on %d of %d minibatch columns, density %.2f, fp32 NumPy/BLAS, %d repeats" % (n, N_PER_GPU, density, done),
+            "ms_per_sample": dt * 1e3}, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--density", type=float, default=0.25)
+    ap.add_argument("--axis", type=int, default=1)
+    ap.add_argument("--sweep", action="store_true", help="also time each op at 5/10/25/50/100 %% density")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3)
+
+    config = {"workload": "BlocksparseMatMul %dx%d block_size=%d density=%.0f%% N=%d/GPU bf16 fprop+bprop+updat (BASELINE configs[1])"
+                          % (C, K, BS, args.density * 100, N_PER_GPU),
+              "feature_axis": args.axis, "layout_seed": SEED, "global_N": N_PER_GPU * world,
+              "parallelism": "dp%d (N-sharded, all-reduce on dW)" % world,
+              "l2": "inputs larger than L2: 3 rotating buffer sets (X,DY,Y,DX per set), 400+ MB"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, dt = cpu_reference(args.density, args.axis, steps=args.steps)
+        line = {"impl": "reference", "metric": "effective TFLOP/s (2*nnz_blocks*bs^2*N, fprop+bprop+updat)", "value": cb["value"],
+                "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from blocksparse_b200 import BlocksparseMatMul, _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16
+    lay = make_layout(args.density)
+    bsmm = BlocksparseMatMul(lay, block_size=BS, feature_axis=args.axis)
+    N = N_PER_GPU
+    gen = torch.Generator(device=dev).manual_seed(SEED + rank)
+    W = (torch.randn(bsmm.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
+    NSETS = 3
+    Xs = [(torch.randn(bsmm.i_shape(N), generator=gen, device=dev) * 0.1).to(dtype) for _ in range(NSETS)]
+    Es = [(torch.randn(bsmm.o_shape(N), generator=gen, device=dev) * 0.1).to(dtype) for _ in range(NSETS)]
+    launches = [0]
+
+    def step(i):
+        x, e = Xs[i % NSETS], Es[i % NSETS]
+        y = bsmm.fprop(x, W)
+        dx = bsmm.bprop(e, W)
+        dw = bsmm.updat([x], [e])
+        launches[0] += 3
+        if world > 1:
+            dist.all_reduce(dw)
+        return y, dx, dw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    kernels = {}
+    bsmm.fprop(Xs[0], W); kernels["fprop"] = _lib.last_kernel()
+    bsmm.bprop(Es[0], W); kernels["bprop"] = _lib.last_kernel()
+    bsmm.updat([Xs[0]], [Es[0]]); kernels["updat"] = _lib.last_kernel()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches[0] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    flops_step_gpu = 3 * 2.0 * bsmm.blocks * BS * BS * N
+    value = flops_step_gpu * world / (ms_per_step * 1e-3) / 1e12
+
+    # ---- per-kernel timing (each kernel alone, rotating inputs) for the roofline object
+    def time_op(fn, reps=20):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    pk = peaks()
+    per_op = {}
+    per_op["fprop"] = time_op(lambda i: bsmm.fprop(Xs[i % NSETS], W))
+    per_op["bprop"] = time_op(lambda i: bsmm.bprop(Es[i % NSETS], W))
+    per_op["updat"] = time_op(lambda i: bsmm.updat([Xs[i % NSETS]], [Es[i % NSETS]]))
+    flops_op = 2.0 * bsmm.blocks * BS * BS * N
+    bytes_op = 2.0 * (C * N + K * N) + 2.0 * bsmm.blocks * BS * BS
+    dom = max(per_op, key=per_op.get)
+    tf = flops_op / (per_op[dom] * 1e-3) / 1e12
+    gbs = bytes_op / (per_op[dom] * 1e-3) / 1e9
+    ridge = pk["tf_burst"] * 1e12 / (pk["hbm"] * 1e9)
+    if flops_op / bytes_op >= ridge:
+        roof = {"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"]}
+    else:
+        roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+    roof.update({"kernel": "%s (%s)" % (dom, kernels[dom]), "traffic": None, "peak_source": pk["source"],
+                 "per_op_ms": per_op,
+                 "per_op_tflops": {k: flops_op / (v * 1e-3) / 1e12 for k, v in per_op.items()},
+                 "per_op_frac_tensor_peak": {k: flops_op / (v * 1e-3) / 1e12 / pk["tf_burst"] for k, v in per_op.items()},
+                 "algorithmic_flops_per_launch": flops_op, "algorithmic_bytes_per_launch": bytes_op})
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    hx = [torch.empty(bsmm.i_shape(N), dtype=dtype).pin_memory() for _ in range(2)]
+    he = [torch.empty(bsmm.o_shape(N), dtype=dtype).pin_memory() for _ in range(2)]
+    for h, s in zip(hx + he, Xs[:2] + Es[:2]):
+        h.copy_(s)
+    hy = torch.empty(bsmm.o_shape(N), dtype=dtype).pin_memory()
+    hdx = torch.empty(bsmm.i_shape(N), dtype=dtype).pin_memory()
+    hdw = torch.empty(bsmm.w_shape, dtype=dtype).pin_memory()
+    w_param = W.clone().requires_grad_()
+
+    def e2e_step(i):
+        x = hx[i % 2].to(dev, non_blocking=True).requires_grad_()
+        e = he[i % 2].to(dev, non_blocking=True)
+        w_param.grad = None
+        y = bsmm(x, w_param)
+        y.backward(e)
+        if world > 1:
+            dist.all_reduce(w_param.grad)
+        hy.copy_(y.detach(), non_blocking=True)
+        hdx.copy_(x.grad, non_blocking=True)
+        hdw.copy_(w_param.grad, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / e2e_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": flops_step_gpu * world / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+           "h2d_bytes_per_step": int(hx[0].numel() * 2 + he[0].numel() * 2),
+           "d2h_bytes_per_step": int(hy.numel() * 2 + hdx.numel() * 2 + hdw.numel() * 2),
+           "ms_per_step": e2e_ms, "api": "BlocksparseMatMul.__call__ + autograd backward, pinned host buffers"}
+
+    sweep = None
+    if args.sweep and rank == 0:
+        sweep = {}
+        for d in (0.05, 0.10, 0.25, 0.50, 1.00):
+            b2 = BlocksparseMatMul(make_layout(d), block_size=BS, feature_axis=args.axis)
+            W2 = (torch.randn(b2.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
+            fl = 2.0 * b2.blocks * BS * BS * N
+            by = 2.0 * (C * N + K * N) + 2.0 * b2.blocks * BS * BS
+            r = {}
+            for name, fn in [("fprop", lambda i: b2.fprop(Xs[i % NSETS], W2)), ("bprop", lambda i: b2.bprop(Es[i % NSETS], W2)),
+                             ("updat", lambda i: b2.updat([Xs[i % NSETS]], [Es[i % NSETS]]))]:
+                m = time_op(fn, reps=10)
+                r[name] = {"ms": m, "tflops": fl / (m * 1e-3) / 1e12, "frac_tensor_peak": fl / (m * 1e-3) / 1e12 / pk["tf_burst"],
+                           "hbm_gbs": by / (m * 1e-3) / 1e9, "frac_hbm_peak": by / (m * 1e-3) / 1e9 / pk["hbm"]}
+            r["nnz_blocks"] = b2.blocks
+            sweep["%d%%" % round(d * 100)] = r
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_reference(args.density, args.axis)
+
+    if rank == 0:
+        line = {"metric": "effective TFLOP/s (2*nnz_blocks*bs^2*N, fprop+bprop+updat)", "value": value, "unit": "TFLOP/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": launches[0], "kernels": kernels, "nnz_blocks": bsmm.blocks,
+                "frac_density_scaled_tensor_peak": value / world / pk["tf_sust"]}
+        if sweep:
+            line["density_sweep"] = sweep
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
