@@ -121,17 +121,18 @@ __global__ void __launch_bounds__(128) probe_gemm(int test, const bf16* Ag, cons
 }
 
 // ----------------------------------------------------------------------------------------------
-// throughput: one thread issues `iters` MMAs; reports SM cycles per MMA.
-enum { B_SS = 0, B_SS_ROT_A, B_SS_COLLECT, B_TS, B_CP_ONLY, B_CP_TS, B_SS_2X };
+// throughput: the elected lane of warp 1 issues `iters` groups of MMAs (warp-uniform control flow,
+// descriptors advanced by adding constants, as a production issue loop does); reports SM cycles per MMA.
+enum { B_SS = 0, B_SS_ROT_A, B_SS_COLLECT, B_TS, B_CP_ONLY, B_CP_TS };
 
-__global__ void __launch_bounds__(128) probe_bench(int mode, int N, int reuse, int iters, long long* cycles, int* status) {
+template <int MODE, int N, int REUSE>
+__global__ void __launch_bounds__(128) probe_bench(int iters, long long* cycles, int* status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid / 32;
-  // 8 A tiles of 8 KB (128 x 32, SW64) and 16 B tiles of up to 16 KB would not fit; B tiles are N x 32 (N*64 B).
-  uint8_t* sA = smem;                        // 8 x 8 KB = 64 KB
-  uint8_t* sB = smem + 65536;                // 4 x 16 KB = 64 KB
+  uint8_t* sA = smem;                        // 8 x 8 KB A tiles (128 x 32, SW64)
+  uint8_t* sB = smem + 65536;                // 4 x 16 KB B tiles (N x 32, SW64)
   for (int i = tid; i < (65536 + 65536) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 0xff);
   if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
   if (warp == 0) { ptx::tmem_alloc(&tmem_base_s, 512); ptx::tmem_relinquish(); }
@@ -140,38 +141,45 @@ __global__ void __launch_bounds__(128) probe_bench(int mode, int N, int reuse, i
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc = ptx::make_idesc_f16(true, false, false, 128, N);
-  long long t0 = 0, t1 = 0;
-  if (tid == 0) {
-    const uint32_t a0 = ptx::smem_u32(sA), b0 = ptx::smem_u32(sB);
-    const int nacc = (512 - 64) / N > 0 ? (512 - 64) / N : 1;        // accumulator regions (cols 64..511), A staging in cols 0..63
-    t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      const int g = it / reuse, j = it % reuse;
-      const uint32_t d = tmem + 64 + (uint32_t)((it % nacc) * N);
-      uint64_t bdesc = ptx::make_smem_desc(b0 + (it & 3) * 16384, 16, 512, ptx::SWZ_64B);
-      uint64_t adesc = ptx::make_smem_desc(a0 + (g & 7) * 8192, 16, 512, ptx::SWZ_64B);
-      switch (mode) {
-        case B_SS:       adesc = ptx::make_smem_desc(a0, 16, 512, ptx::SWZ_64B); ptx::mma_ss(d, adesc, bdesc, idesc, 1); break;
-        case B_SS_ROT_A: adesc = ptx::make_smem_desc(a0 + (it & 7) * 8192, 16, 512, ptx::SWZ_64B); ptx::mma_ss(d, adesc, bdesc, idesc, 1); break;
-        case B_SS_COLLECT:
-          if (reuse == 1) ptx::mma_ss(d, adesc, bdesc, idesc, 1);
-          else if (j == 0) ptx::mma_ss_a_fill(d, adesc, bdesc, idesc, 1);
-          else if (j == reuse - 1) ptx::mma_ss_a_lastuse(d, adesc, bdesc, idesc, 1);
-          else ptx::mma_ss_a_use(d, adesc, bdesc, idesc, 1);
-          break;
-        case B_TS:       ptx::mma_ts(d, tmem + (g & 7) * 8, bdesc, idesc, 1); break;
-        case B_CP_ONLY:  ptx::tc_cp_128x256b(tmem + (it & 7) * 8, adesc); break;
-        case B_CP_TS:
-          if (j == 0) ptx::tc_cp_128x256b(tmem + (g & 7) * 8, adesc);
-          ptx::mma_ts(d, tmem + (g & 7) * 8, bdesc, idesc, 1);
-          break;
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int NACC = (448 / N) > 0 ? (448 / N) : 1;     // accumulators in columns 64.., A staging in 0..63
+  if (warp == 1) {
+    const uint64_t a_base = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 512, ptx::SWZ_64B);
+    const uint64_t b_base = ptx::make_smem_desc(ptx::smem_u32(sB), 16, 512, ptx::SWZ_64B);
+    long long t0 = clock64();
+    if (ptx::elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                      // 8 groups per iteration, each REUSE MMAs on one A
+          const uint64_t adesc = a_base + (uint64_t)(u * (8192 >> 4));
+#pragma unroll
+          for (int j = 0; j < REUSE; ++j) {
+            const int q = u * REUSE + j;
+            const uint32_t d = tmem + 64 + (uint32_t)((q % NACC) * N);
+            const uint64_t bdesc = b_base + (uint64_t)((q & 3) * (16384 >> 4));
+            if (MODE == B_SS) ptx::mma_ss(d, a_base, bdesc, idesc, 1);
+            if (MODE == B_SS_ROT_A) ptx::mma_ss(d, a_base + (uint64_t)((q & 7) * (8192 >> 4)), bdesc, idesc, 1);
+            if (MODE == B_SS_COLLECT) {
+              if (REUSE == 1) ptx::mma_ss(d, adesc, bdesc, idesc, 1);
+              else if (j == 0) ptx::mma_ss_a_fill(d, adesc, bdesc, idesc, 1);
+              else if (j == REUSE - 1) ptx::mma_ss_a_lastuse(d, adesc, bdesc, idesc, 1);
+              else ptx::mma_ss_a_use(d, adesc, bdesc, idesc, 1);
+            }
+            if (MODE == B_TS) ptx::mma_ts(d, tmem + u * 8, bdesc, idesc, 1);
+            if (MODE == B_CP_ONLY) ptx::tc_cp_128x256b(tmem + (q & 7) * 8, adesc);
+            if (MODE == B_CP_TS) {
+              if (j == 0) ptx::tc_cp_128x256b(tmem + u * 8, adesc);
+              ptx::mma_ts(d, tmem + u * 8, bdesc, idesc, 1);
+            }
+          }
+        }
       }
+      ptx::tc_commit(&bar);
     }
-    ptx::tc_commit(&bar);
+    __syncwarp();
     if (!ptx::mbar_wait(&bar, 0)) status[0] = 3;
-    t1 = clock64();
-    cycles[blockIdx.x] = t1 - t0;
+    long long t1 = clock64();
+    if (tid == 32) cycles[blockIdx.x] = t1 - t0;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -252,38 +260,50 @@ static int run_gemm(int test, const char* name) {
   return (status == 0 && maxerr < 1e-3) ? 0 : 1;
 }
 
+template <int MODE, int N, int REUSE>
+static void bench_one(const char* name, long long* cyc, int* st) {
+  const int iters = 256;
+  CK(cudaFuncSetAttribute(probe_bench<MODE, N, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+  for (int grid : {1, 148}) {
+    CK(cudaMemset(cyc, 0, 148 * 8));
+    probe_bench<MODE, N, REUSE><<<grid, 128, 131072>>>(iters, cyc, st);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("bench %-22s grid=%d LAUNCH ERROR %s\n", name, grid, cudaGetErrorString(e)); exit(1); }
+    std::vector<long long> h(148);
+    CK(cudaMemcpy(h.data(), cyc, 148 * 8, cudaMemcpyDeviceToHost));
+    long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+    int status; CK(cudaMemcpy(&status, st, 4, cudaMemcpyDeviceToHost));
+    const double per = (double)mx / (iters * 8.0 * REUSE);
+    const double ideal = MODE == B_CP_ONLY ? 0 : 128.0 * N / 256.0;
+    printf("bench %-22s grid=%3d cycles/op=%7.2f  ideal_mma=%5.1f  eff=%5.1f%% status=%d\n", name, grid, per, ideal,
+           ideal > 0 ? 100.0 * ideal / per : 0.0, status);
+  }
+}
+
 static void run_bench() {
   long long* cyc; int* st;
   CK(cudaMalloc(&cyc, 148 * 8)); CK(cudaMalloc(&st, 4)); CK(cudaMemset(st, 0, 4));
-  CK(cudaFuncSetAttribute(probe_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
-  struct Cfg { int mode, N, reuse; const char* name; };
-  Cfg cfgs[] = {
-    {B_SS, 32, 1, "ss same-A N=32"}, {B_SS, 64, 1, "ss same-A N=64"}, {B_SS, 128, 1, "ss same-A N=128"}, {B_SS, 256, 1, "ss same-A N=256"},
-    {B_SS_ROT_A, 32, 1, "ss rot-A N=32"}, {B_SS_ROT_A, 64, 1, "ss rot-A N=64"}, {B_SS_ROT_A, 128, 1, "ss rot-A N=128"},
-    {B_SS_COLLECT, 32, 2, "ss collect r=2 N=32"}, {B_SS_COLLECT, 32, 4, "ss collect r=4 N=32"}, {B_SS_COLLECT, 32, 8, "ss collect r=8 N=32"},
-    {B_SS_COLLECT, 64, 4, "ss collect r=4 N=64"},
-    {B_TS, 32, 4, "ts N=32"}, {B_TS, 64, 4, "ts N=64"}, {B_TS, 128, 4, "ts N=128"},
-    {B_CP_ONLY, 32, 1, "cp 128x256b only"},
-    {B_CP_TS, 32, 1, "cp+ts r=1 N=32"}, {B_CP_TS, 32, 2, "cp+ts r=2 N=32"}, {B_CP_TS, 32, 4, "cp+ts r=4 N=32"}, {B_CP_TS, 32, 8, "cp+ts r=8 N=32"},
-    {B_CP_TS, 64, 4, "cp+ts r=4 N=64"},
-  };
-  const int iters = 4096;
-  for (int grid : {1, 148}) {
-    for (const Cfg& c : cfgs) {
-      CK(cudaMemset(cyc, 0, 148 * 8));
-      probe_bench<<<grid, 128, 131072>>>(c.mode, c.N, c.reuse, iters, cyc, st);
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) { printf("bench %-22s grid=%d LAUNCH ERROR %s\n", c.name, grid, cudaGetErrorString(e)); exit(1); }
-      std::vector<long long> h(148);
-      CK(cudaMemcpy(h.data(), cyc, 148 * 8, cudaMemcpyDeviceToHost));
-      long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-      int status; CK(cudaMemcpy(&status, st, 4, cudaMemcpyDeviceToHost));
-      const double per = (double)mx / iters;
-      const double ideal = c.mode == B_CP_ONLY ? 0 : 128.0 * c.N / 256.0;
-      printf("bench %-22s grid=%3d cycles/op=%7.2f  ideal_mma=%5.1f  eff=%5.1f%% status=%d\n", c.name, grid, per, ideal,
-             ideal > 0 ? 100.0 * ideal / per : 0.0, status);
-    }
-  }
+  bench_one<B_SS, 32, 1>("ss same-A N=32", cyc, st);
+  bench_one<B_SS, 64, 1>("ss same-A N=64", cyc, st);
+  bench_one<B_SS, 128, 1>("ss same-A N=128", cyc, st);
+  bench_one<B_SS, 256, 1>("ss same-A N=256", cyc, st);
+  bench_one<B_SS_ROT_A, 32, 1>("ss rot-A N=32", cyc, st);
+  bench_one<B_SS_ROT_A, 64, 1>("ss rot-A N=64", cyc, st);
+  bench_one<B_SS_ROT_A, 128, 1>("ss rot-A N=128", cyc, st);
+  bench_one<B_SS_ROT_A, 256, 1>("ss rot-A N=256", cyc, st);
+  bench_one<B_SS_COLLECT, 32, 2>("ss collect r=2 N=32", cyc, st);
+  bench_one<B_SS_COLLECT, 32, 4>("ss collect r=4 N=32", cyc, st);
+  bench_one<B_SS_COLLECT, 32, 8>("ss collect r=8 N=32", cyc, st);
+  bench_one<B_SS_COLLECT, 64, 4>("ss collect r=4 N=64", cyc, st);
+  bench_one<B_TS, 32, 4>("ts N=32", cyc, st);
+  bench_one<B_TS, 64, 4>("ts N=64", cyc, st);
+  bench_one<B_TS, 128, 4>("ts N=128", cyc, st);
+  bench_one<B_CP_ONLY, 32, 1>("cp 128x256b only", cyc, st);
+  bench_one<B_CP_TS, 32, 1>("cp+ts r=1 N=32", cyc, st);
+  bench_one<B_CP_TS, 32, 2>("cp+ts r=2 N=32", cyc, st);
+  bench_one<B_CP_TS, 32, 4>("cp+ts r=4 N=32", cyc, st);
+  bench_one<B_CP_TS, 32, 8>("cp+ts r=8 N=32", cyc, st);
+  bench_one<B_CP_TS, 64, 4>("cp+ts r=4 N=64", cyc, st);
 }
 
 int main(int argc, char** argv) {
