@@ -22,9 +22,10 @@ SIGNATURES = {
     "bsmm_last_error": (_c.c_char_p, []),
     "bsmm_last_kernel": (_c.c_char_p, []),
     "bsmm_device_info": (_i, [_c.POINTER(_i)] * 3),
-    "bsmm_xprop": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "bsmm_device_error": (_i, []),
+    "bsmm_xprop": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bsmm_updat": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i,
-                        _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _vp]),
+                        _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "bsmm_gate_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "bst_nt": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "bst_xn": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -65,6 +66,11 @@ def check(rc, what):
         if rc < 0:
             raise ValueError("%s failed (%d): %s" % (what, rc, msg))
         raise BsmmError("%s failed (cuda error %d): %s" % (what, rc, msg))
+
+
+def device_error():
+    """Synchronise and return (then clear) the sticky device-side error word; 0 means no kernel timed out."""
+    return load().bsmm_device_error()
 
 
 def last_kernel():

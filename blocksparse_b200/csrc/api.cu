@@ -22,6 +22,14 @@ int bsmm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return 0;
 }
 
+int bsmm_device_error(void) {
+  int v = 0, zero = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int)) != cudaSuccess) return -1;
+  if (v != 0) cudaMemcpyToSymbol(g_tc_error, &zero, sizeof(int));
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------
 static int check_bsize_axis(int bsize, int axis) {
   if (axis != 0 && axis != 1) return fail(BSMM_E_BSIZE, "feature axis must be 0 or 1, got %d", axis);
@@ -34,7 +42,7 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
                const int32_t* lut, int n_out, int n_in, int blocks,
                const void* x, const void* w, void* y, int N,
                const float* gate,
-               const int32_t* sched, int sched_len,
+               const int32_t* sched, int sched_tiles, int sched_tile_blocks, int sched_groups_off,
                int flags, void* stream) {
   if (int e = check_bsize_axis(bsize, axis)) return e;
   if (!lut || !x || !w || !y) return fail(BSMM_E_ARG, "bsmm_xprop: null pointer");
@@ -45,7 +53,7 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
   cudaStream_t s = (cudaStream_t)stream;
 
   if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
-    int rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_len, s);
+    int rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_tiles, sched_tile_blocks, sched_groups_off, s);
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC)
       return fail(BSMM_E_ARG, "bsmm_xprop: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());
@@ -73,7 +81,7 @@ int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
                const void* const* xs, const void* const* dys, int pcount,
                void* dw, int N, float alpha, float beta,
                const float* gate, int gated_dw,
-               const int32_t* sched, int sched_len,
+               const int32_t* sched, int sched_tiles, int sched_tile_blocks, int sched_groups_off,
                int flags, void* stream) {
   if (int e = check_bsize_axis(bsize, axis)) return e;
   if (!updat_lut || !xs || !dys || !dw) return fail(BSMM_E_ARG, "bsmm_updat: null pointer");
@@ -88,7 +96,7 @@ int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
 
   if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
     int rc = tc_updat(dtype, dw_dtype, axis, bsize, updat_lut, blocks, n_c_blocks, n_k_blocks, xs, dys, pcount,
-                      dw, N, alpha, beta, gate, gated_dw, sched, sched_len, s);
+                      dw, N, alpha, beta, gate, gated_dw, sched, sched_tiles, sched_tile_blocks, sched_groups_off, s);
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC)
       return fail(BSMM_E_ARG, "bsmm_updat: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());

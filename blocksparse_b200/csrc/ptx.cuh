@@ -50,12 +50,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: returns false if the barrier did not flip within ~2^26 polls (a few seconds)
-// so that a protocol bug surfaces as an error flag instead of hanging the GPU.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 26); ++i)
-    if (mbar_try_wait(bar, parity)) return true;
-  return false;
+// Bounded wait: returns false if the barrier did not flip within ~2 s of wall clock, so that a
+// protocol bug surfaces as an error instead of hanging the GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// `abort_flag` (shared memory) is raised by whichever wait times out first, and makes every other
+// wait of the CTA return immediately so a deadlock costs one timeout, not one per wait.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait(bar, parity)) return true;
+    if (abort_flag && *abort_flag) return false;
+    if (globaltimer_ns() - t0 > 500000000ull) {
+      if (abort_flag) *abort_flag = 1;
+      return false;
+    }
+  }
 }
 
 // ---- TMA ---------------------------------------------------------------------------------

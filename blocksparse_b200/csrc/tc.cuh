@@ -1,15 +1,347 @@
-// tcgen05 kernel families (filled in below); returns TC_NOT_APPLICABLE when the
-// configuration has no tensor-core kernel so that the caller uses the CUDA-core family.
+// tcgen05 (5th-gen tensor core) kernel families for sm_100a.
+//
+// tc_xprop: block-sparse fprop / bprop for 16-bit dtypes, feature_axis = 1, block size 32 / 64.
+//   Replaces hgemm_blocksparse_64x64x64_nx_dsd / 64x32x32_nx_dsd
+//   (reference src/blocksparse_hgemm_nc_op_gpu.cu:38-551).
+//
+// Formulation (see DESIGN.md "xprop on tcgen05"): the minibatch sits on the MMA M axis (128 rows per
+// CTA tile), one W block is the B operand (N = K = block size), and an output tile covers up to
+// 512/bs consecutive output blocks whose fp32 accumulators fill the CTA's tensor memory.  The tile
+// schedule (blocksparse_b200/lut.py:build_tile_schedule) groups the LUT by INPUT block, so an
+// activation tile is staged once by TMA and every block that consumes it is issued back to back with
+// the A-operand collector hints (fill / use / lastuse): the B200 probe (profiles/r1_tc_probe.txt)
+// shows an N=32 MMA is shared-memory bound at 40 cycles when A is re-read, 16 + 27/R with reuse R.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer: activation tiles (4-stage ring) and W blocks (32-stage ring)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  epilogue: tcgen05.ld -> 16-bit -> swizzled smem staging -> TMA store
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace bsmm {
 constexpr int TC_NOT_APPLICABLE = -1000;
 
-inline int tc_xprop(int, int, int, int, const int32_t*, int, int, int, const void*, const void*, void*, int,
-                    const float*, const int32_t*, int, cudaStream_t) { return TC_NOT_APPLICABLE; }
+// ---- TMA descriptor encoding via the driver entry point (no -lcuda link dependency) -----------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = []() -> TmapEncodeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+// 2-D row-major 16-bit tensor [outer][inner]; box = box_outer rows x box_inner elements.
+inline int make_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_elems,
+                        uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return fail(BSMM_E_NODEV, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = dtype == BSMM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BSMM_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipeline protocol.  One pipeline stage == one schedule GROUP (lut.py:build_tile_schedule): the
+// activation tile of one input block plus the <= WPS W blocks of the output tile that consume it, all
+// landing on ONE mbarrier.  Every per-block decision (accumulator column, accumulate flag, A-collector
+// hint, merging of adjacent blocks into one wider MMA) is precomputed on the host into a 128-byte
+// group record, because the first profile (profiles/r1_xprop_v1_ncu.txt) showed both the producer and
+// the single issuing thread instruction-bound at hundreds of cycles per block when they derived them.
+//   producer warps (2, alternating groups): one coalesced 128-byte load per group, prefetched a group
+//     ahead; lanes 4..11 each issue one W TMA load; lanes 12..27 copy the run commands to smem
+//   MMA warp: one barrier wait per group, then one LDS.64 + one tcgen05.mma per run and K slice
+template <int BS> struct XpropCfg;
+template <> struct XpropCfg<32> {
+  static constexpr int XS = 6, WPS = 8, STG = 8;               // group stages, W slots per stage, staging buffers
+  static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;     // 64-byte rows
+};
+template <> struct XpropCfg<64> {
+  static constexpr int XS = 3, WPS = 4, STG = 4;
+  static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;   // 128-byte rows
+};
+constexpr int XPROP_PRODUCERS = 2;
+constexpr int XPROP_THREADS = (XPROP_PRODUCERS + 1 + 4) * 32;
+
+// sticky device-side error word: a kernel whose bounded wait timed out stores a non-zero code here
+__device__ int g_tc_error = 0;
+
+struct XpropTcParams {
+  const int32_t* sched;      // tile schedule (lut.py:build_tile_schedule)
+  int groups_off;            // int32 index of the first group record
+  int n_ktiles;              // output tiles along the feature axis
+  int n_ntiles;              // ceil(N / 128)
+  int bprop;
+};
+struct XpropTmaps { CUtensorMap x, w, y; };
+
+template <int BS, bool BF16>
+__global__ void __launch_bounds__(XPROP_THREADS, 1)
+tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) {
+  using Cfg = XpropCfg<BS>;
+  constexpr int XS = Cfg::XS, WPS = Cfg::WPS, STG = Cfg::STG;
+  constexpr int KS = BS / 16;                     // K=16 slices per block
+  constexpr uint32_t XBYTES = 128 * BS * 2, WBYTES = BS * BS * 2;
+  constexpr uint32_t STAGE_BYTES = XBYTES + WPS * WBYTES;
+  constexpr uint32_t ROW = BS * 2;                // bytes per smem row (== swizzle span)
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sStage = smem;                         // XS x (activation tile | WPS W blocks)
+  uint8_t* sO = smem + XS * STAGE_BYTES;          // STG x XBYTES staging for the output tile
+  __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty;
+  __shared__ int2 cmd[XS][8];                     // run commands of the group in each stage
+  __shared__ int cmd_n[XS];                       // number of runs
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
+  volatile int* abort_flag = &abort_s;
+
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int total_tiles = p.n_ktiles * p.n_ntiles;
+  const int32_t* sched = p.sched;
+
+  if (tid == 0) {
+    abort_s = 0;
+    for (int i = 0; i < XS; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(&acc_full, 1);
+    ptx::mbar_init(&acc_empty, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tensormap(&maps.x); ptx::prefetch_tensormap(&maps.w); ptx::prefetch_tensormap(&maps.y);
+  }
+  if (warp == XPROP_PRODUCERS) { ptx::tmem_alloc(&tmem_base_s, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < XPROP_PRODUCERS) {
+    // ================================ TMA producers ================================
+    // Producer `warp` owns the groups whose running index gc (over all tiles of this CTA) has
+    // gc % XPROP_PRODUCERS == warp; lane i holds int i of the group record.
+    uint32_t gbase = 0;                   // groups of earlier tiles
+    bool alive = true;
+    for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
+      const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
+      const int32_t* th = sched + 4 + 4 * kt;
+      const int first_group = th[0], n_groups = th[1];
+      const int32_t* grec = sched + p.groups_off + (size_t)first_group * 32;
+      // first group of this tile owned by this warp
+      int g = (int)((XPROP_PRODUCERS + warp - (gbase % XPROP_PRODUCERS)) % XPROP_PRODUCERS);
+      int rec = (g < n_groups) ? grec[g * 32 + lane] : 0;
+      for (; g < n_groups; g += XPROP_PRODUCERS) {
+        const int cur = rec;
+        const int gn = g + XPROP_PRODUCERS;
+        if (gn < n_groups) rec = grec[gn * 32 + lane];          // prefetch the next record
+        const uint32_t gc = gbase + g;
+        const uint32_t st = gc % XS;
+        const int in_blk = __shfl_sync(0xffffffffu, cur, 0);
+        const int counts = __shfl_sync(0xffffffffu, cur, 1);
+        const int n_w = counts & 0xff, n_runs = counts >> 8;
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(&empty[st], ((gc / XS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
+        if (lane >= 12 && lane < 12 + 2 * n_runs) reinterpret_cast<int*>(&cmd[st][0])[lane - 12] = cur;
+        if (lane == 0) cmd_n[st] = n_runs;
+        __syncwarp();
+        uint8_t* stage = sStage + st * STAGE_BYTES;
+        if (lane == 0) {
+          ptx::mbar_expect_tx(&full[st], XBYTES + (uint32_t)n_w * WBYTES);
+          ptx::tma_load_2d(stage, &maps.x, &full[st], in_blk * BS, nt * 128);
+        }
+        if (lane >= 4 && lane < 4 + n_w)
+          ptx::tma_load_2d(stage + XBYTES + (lane - 4) * WBYTES, &maps.w, &full[st], 0, cur * BS);
+        __syncwarp();
+      }
+      gbase += n_groups;
+    }
+  } else if (warp == XPROP_PRODUCERS) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc0 = ptx::make_idesc_f16(BF16, false, !p.bprop, 128, 0);
+    // fprop: B = W[c][k] read as K x N with N contiguous (MN-major): K=16 slice = 16 rows, blocks LBO apart.
+    // bprop: B = W[c][k] read as N x K with K contiguous (K-major):  K=16 slice = 32 bytes along the row.
+    const uint32_t b_kstep16 = (p.bprop ? 32u : 16u * ROW) >> 4;
+    const uint64_t a_desc0 = ptx::make_smem_desc(ptx::smem_u32(sStage), 16, Cfg::SBO, Cfg::SWZ);
+    const uint64_t b_desc0 = ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
+    uint32_t gc = 0, tile_it = 0;
+    bool alive = true;
+    for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x, ++tile_it) {
+      const int kt = t % p.n_ktiles;
+      const int n_groups = sched[4 + 4 * kt + 1];
+      if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, (tile_it & 1) ^ 1, abort_flag))) { g_tc_error = 3; break; }
+      ptx::tc_fence_after();
+      for (int g = 0; g < n_groups; ++g, ++gc) {
+        const uint32_t st = gc % XS;
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(&full[st], (gc / XS) & 1, abort_flag))) { g_tc_error = 4; alive = false; break; }
+        ptx::tc_fence_after();
+        const int n_runs = cmd_n[st];
+        if (ptx::elect_one()) {
+          const uint64_t a_st = a_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
+          const uint64_t b_st = b_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t adesc = a_st + (uint64_t)(ks * 2);
+#pragma unroll 1
+            for (int r = 0; r < n_runs; ++r) {
+              const int2 c = cmd[st][r];
+              const uint64_t bdesc = b_st + (uint64_t)(((uint32_t)c.x & 0xffffu) + ks * b_kstep16);
+              const uint32_t d = tmem + ((uint32_t)c.x >> 16);
+              const uint32_t idesc = idesc0 | (((uint32_t)c.y & 0xffu) << 17);
+              const uint32_t acc = (ks > 0) ? 1u : (((uint32_t)c.y >> 8) & 1u);
+              const uint32_t hint = (uint32_t)c.y >> 16;
+              if (hint == 0)      ptx::mma_ss(d, adesc, bdesc, idesc, acc);
+              else if (hint == 1) ptx::mma_ss_a_fill(d, adesc, bdesc, idesc, acc);
+              else if (hint == 2) ptx::mma_ss_a_use(d, adesc, bdesc, idesc, acc);
+              else                ptx::mma_ss_a_lastuse(d, adesc, bdesc, idesc, acc);
+            }
+          }
+          ptx::tc_commit(&empty[st]);       // the stage is free once these MMAs retire
+        }
+        __syncwarp();
+      }
+      if (ptx::elect_one()) ptx::tc_commit(&acc_full);
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;                  // row of the 128-row tile
+    const int etid = (warp - XPROP_PRODUCERS - 1) * 32 + lane;
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
+      const int32_t* th = sched + 4 + 4 * kt;
+      const int first_out = th[2];
+      const int n_out = th[3] & 0xff;
+      const uint32_t mask = (uint32_t)th[3] >> 8;
+      ptx::mbar_wait(&acc_full, tile_it & 1, abort_flag);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*abort_flag) { g_tc_error = 6; break; }       // uniform across the 128 epilogue threads
+      ptx::tc_fence_after();
+      for (int s0 = 0; s0 < n_out; s0 += STG) {
+        // the staging buffers must have been drained by the TMA stores issued before
+        if (etid == 0) ptx::tma_store_wait_read<0>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int s1 = min(n_out, s0 + STG);
+        for (int slot = s0; slot < s1; ++slot) {
+          uint8_t* dst = sO + (slot - s0) * XBYTES + row * ROW;
+#pragma unroll
+          for (int h = 0; h < BS / 32; ++h) {            // 32 fp32 columns at a time
+            uint32_t v[32];
+            if ((mask >> slot) & 1u) {
+              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
+              ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;    // output block with an empty LUT row
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                // four 16-byte chunks (8 elements each)
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = __uint_as_float(v[c * 8 + 2 * e]), b = __uint_as_float(v[c * 8 + 2 * e + 1]);
+                if (BF16) { __nv_bfloat162 q = __floats2bfloat162_rn(a, b); pk[e] = *reinterpret_cast<uint32_t*>(&q); }
+                else      { __half2 q = __floats2half2_rn(a, b);           pk[e] = *reinterpret_cast<uint32_t*>(&q); }
+              }
+              const uint32_t chunk = h * 4 + c;                                  // 16-byte chunk index in the row
+              const uint32_t swz = (BS == 32) ? (chunk ^ ((row >> 1) & 3)) : (chunk ^ (row & 7));
+              *reinterpret_cast<uint4*>(dst + swz * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          if (s1 == n_out) ptx::mbar_arrive(&acc_empty);     // accumulators are free for the next tile
+          for (int slot = s0; slot < s1; ++slot)
+            ptx::tma_store_2d(&maps.y, sO + (slot - s0) * XBYTES, (first_out + slot) * BS, nt * 128);
+          ptx::tma_store_commit();
+        }
+      }
+    }
+    if (etid == 0) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == XPROP_PRODUCERS) ptx::tmem_dealloc(tmem, 512);
+}
+
+template <int BS>
+constexpr size_t xprop_smem_bytes() {
+  using Cfg = XpropCfg<BS>;
+  return (size_t)Cfg::XS * (128 * BS * 2 + Cfg::WPS * BS * BS * 2) + (size_t)Cfg::STG * 128 * BS * 2;
+}
+
+template <int BS, bool BF16>
+int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count, cudaStream_t s) {
+  auto kern = tc_xprop_kernel<BS, BF16>;
+  constexpr size_t smem = xprop_smem_bytes<BS>();
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int total = p.n_ktiles * p.n_ntiles;
+  const int grid = total < sm_count ? total : sm_count;
+  kern<<<grid, XPROP_THREADS, smem, s>>>(p, maps);
+  return check_launch(BS == 32 ? "tcgen05_xprop_bs32" : "tcgen05_xprop_bs64");
+}
+
+inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lut, int n_out, int n_in, int blocks,
+                    const void* x, const void* w, void* y, int N, const float* gate, const int32_t* sched, int sched_tiles, int sched_tile_blocks,
+                    int sched_groups_off, cudaStream_t s) {
+  (void)lut;
+  if (dtype != BSMM_F16 && dtype != BSMM_BF16) { fail(0, "fp32 runs on the FMA path"); return TC_NOT_APPLICABLE; }
+  if (axis != 1) { fail(0, "feature_axis 0 has no tcgen05 xprop kernel yet"); return TC_NOT_APPLICABLE; }
+  if (bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
+  if (gate != nullptr) { fail(0, "gated xprop uses the CUDA-core path"); return TC_NOT_APPLICABLE; }
+  if (sched == nullptr || sched_tiles <= 0) { fail(0, "no tile schedule supplied"); return TC_NOT_APPLICABLE; }
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) { fail(0, "pointers must be 16-byte aligned for TMA"); return TC_NOT_APPLICABLE; }
+  const DeviceInfo& dev = device_info();
+  if (!dev.ok || dev.cc_major != 10) { fail(0, "tcgen05 needs an sm_100 device"); return TC_NOT_APPLICABLE; }
+
+  // cuTensorMapEncodeTiled is a driver entry point: make sure this host thread (e.g. an autograd
+  // worker) has the primary context bound before calling it
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const uint64_t Cin = (uint64_t)n_in * bsize, Cout = (uint64_t)n_out * bsize;
+  XpropTmaps maps;
+  const CUtensorMapSwizzle swz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (int e = make_tmap_2d(&maps.x, dtype, x, Cin, (uint64_t)N, Cin, bsize, 128, swz)) return e;
+  if (int e = make_tmap_2d(&maps.w, dtype, w, (uint64_t)bsize, (uint64_t)blocks * bsize, (uint64_t)bsize, bsize, bsize, swz)) return e;
+  if (int e = make_tmap_2d(&maps.y, dtype, y, Cout, (uint64_t)N, Cout, bsize, 128, swz)) return e;
+
+  XpropTcParams p;
+  p.sched = sched;
+  p.n_ntiles = (N + 127) / 128;
+  p.bprop = bprop;
+  // the schedule itself lives in device memory; its shape is passed by value
+  p.n_ktiles = sched_tiles;
+  p.groups_off = sched_groups_off;
+  const int tile_blocks = sched_tile_blocks;
+  if (p.n_ktiles <= 0 || tile_blocks <= 0 || tile_blocks > 512 / bsize || p.n_ktiles * tile_blocks < n_out ||
+      sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
+    return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
+                p.n_ktiles, tile_blocks, n_out);
+  if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true>(p, maps, dev.sm_count, s)
+                                             : launch_tc_xprop<32, false>(p, maps, dev.sm_count, s);
+  return dtype == BSMM_BF16 ? launch_tc_xprop<64, true>(p, maps, dev.sm_count, s)
+                            : launch_tc_xprop<64, false>(p, maps, dev.sm_count, s);
+}
+
 inline int tc_updat(int, int, int, int, const int32_t*, int, int, int, const void* const*, const void* const*, int,
-                    void*, int, float, float, const float*, int, const int32_t*, int, cudaStream_t) { return TC_NOT_APPLICABLE; }
+                    void*, int, float, float, const float*, int, const int32_t*, int, int, int, cudaStream_t) { return TC_NOT_APPLICABLE; }
 inline int tc_bst_nt(int, int, int, const int32_t*, int, int, const void*, const void*, void*, int, int, int, int, int,
                      cudaStream_t) { return TC_NOT_APPLICABLE; }
 inline int tc_bst_xn(int, int, int, int, const int32_t*, int, int, int, const void*, const void*, void*, int, int, int,

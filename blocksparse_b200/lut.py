@@ -163,65 +163,115 @@ class MatmulLuts(object):
         self.bprop_rows, self.bprop_max = row_lut(b[0], b[1], b[2], CB)
         self._f, self._b = f, b
 
-    def tile_schedule(self, bprop, blocks_per_tile):
+    def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8):
         outs, ins, wids = self._b if bprop else self._f
         n_out = self.CB if bprop else self.KB
-        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile)
+        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group)
 
 
-def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile):
+GROUP_INTS = 32          # one 128-byte record per schedule group (one coalesced warp load)
+GROUP_MAX_W = 8          # W blocks per group record (ints 4..11)
+GROUP_MAX_RUNS = 8       # MMA runs per group record (ints 12..27, two ints each)
+
+
+def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per_group=8):
     """Schedule for the tcgen05 xprop kernel (csrc/tc.cuh).
 
-    An output tile covers `blocks_per_tile` consecutive output blocks (their fp32
-    accumulators live side by side in tensor memory).  For every tile the schedule
-    lists each input block that feeds at least one of them ONCE, followed by the
-    (slot, w) pairs that consume it, so the kernel stages an activation tile a single
-    time and issues one MMA per pair against it.
+    An output tile covers `blocks_per_tile` consecutive output blocks (their fp32 accumulators live
+    side by side in tensor memory, block s of the tile at columns [s*bsize, (s+1)*bsize)).  For every
+    tile the LUT is regrouped by INPUT block: a *group* is one activation tile plus the <= w_per_group
+    W blocks of the tile that consume it (an input block with more consumers is split into several
+    groups).  Everything the device loops would otherwise derive per block is precomputed here:
+
+      * W blocks are listed in accumulator order and staged in consecutive shared-memory slots, so
+        blocks whose accumulators are adjacent form a *run* that is issued as ONE wider MMA
+        (N = run_len*bsize); a dense layout degenerates to ordinary wide GEMM instructions;
+      * the accumulate flag of every run (0 = first touch of those accumulators in this tile) -- runs
+        are split where the flag changes;
+      * the A-collector hint of every run (0 plain, 1 fill, 2 use, 3 last use).
 
     int32 layout:
-      [0] n_tiles  [1] blocks_per_tile  [2] total groups  [3] total pairs
-      tile header   [n_tiles][4]  = (first_group, n_groups, first_out_block, n_out_blocks)
-      group records [groups ][4]  = (in_block, first_pair, n_pairs, 0)
-      pair records  [pairs  ][2]  = (slot_in_tile, w_block)
-    first_group / first_pair are absolute int32 offsets into the array.
+      [0] n_tiles  [1] blocks_per_tile  [2] total groups  [3] total W loads
+      tile header   [n_tiles][4] = (first_group_index, n_groups, first_out_block, n_out | touched_mask << 8)
+      (padding to a multiple of GROUP_INTS ints)
+      group records [groups][32]:
+          [0] in_block   [1] n_w | n_runs << 8   [2..3] reserved
+          [4..11]  W block ids, in staging-slot order
+          [12..27] runs, two ints each:
+                   int0 = (w_slot * bsize*bsize*2) >> 4  |  (accumulator column << 16)
+                   int1 = (N >> 3) | accumulate << 8 | collector_hint << 16
+    Returns (schedule, groups_offset): groups_offset is the int32 index of the first group record.
     """
     T = int(blocks_per_tile)
+    assert 1 <= w_per_group <= GROUP_MAX_W
     n_tiles = ceil_div(n_out, T)
     outs = np.asarray(outs, dtype=np.int64)
     ins = np.asarray(ins, dtype=np.int64)
     wids = np.asarray(wids, dtype=np.int64)
+    nnz = len(outs)
     tile = outs // T
     order = np.lexsort((outs, ins, tile))          # by tile, then input block, then slot
     tile_s, ins_s, outs_s, w_s = tile[order], ins[order], outs[order], wids[order]
-    nnz = len(outs)
-    new_group = np.ones(nnz, dtype=bool)
+    slot_s = outs_s - tile_s * T
+
+    # position of each pair inside its (tile, in_block) cluster -> chunk of w_per_group pairs = group
+    new_cluster = np.ones(nnz, dtype=bool)
     if nnz:
-        new_group[1:] = (tile_s[1:] != tile_s[:-1]) | (ins_s[1:] != ins_s[:-1])
+        new_cluster[1:] = (tile_s[1:] != tile_s[:-1]) | (ins_s[1:] != ins_s[:-1])
+    cluster_id = np.cumsum(new_cluster) - 1
+    cluster_start = np.nonzero(new_cluster)[0]
+    pos_in_cluster = np.arange(nnz) - cluster_start[cluster_id]
+    new_group = new_cluster | (pos_in_cluster % w_per_group == 0)
+    group_id = np.cumsum(new_group) - 1
     g_first = np.nonzero(new_group)[0]
     n_groups = len(g_first)
     g_count = np.diff(np.concatenate((g_first, [nnz])))
-    g_tile = tile_s[g_first]
-    groups_per_tile = np.bincount(g_tile, minlength=n_tiles)
-    tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
+    pos_in_group = np.arange(nnz) - g_first[group_id]
 
-    hdr_off = 4
-    grp_off = hdr_off + 4 * n_tiles
-    pair_off = grp_off + 4 * n_groups
-    sched = np.zeros(pair_off + 2 * nnz, dtype=np.int32)
+    # first touch of an accumulator slot inside its tile: earliest pair (in processing order) of (tile, slot)
+    key = tile_s * T + slot_s
+    first_idx = np.full(n_tiles * T, nnz, dtype=np.int64)
+    np.minimum.at(first_idx, key, np.arange(nnz))
+    accumulate = (np.arange(nnz) != first_idx[key]).astype(np.int64)
+
+    # runs: consecutive pairs of a group with consecutive slots and equal accumulate flag
+    new_run = np.ones(nnz, dtype=bool)
+    if nnz:
+        new_run[1:] = new_group[1:] | (slot_s[1:] != slot_s[:-1] + 1) | (accumulate[1:] != accumulate[:-1])
+    run_first = np.nonzero(new_run)[0]
+    run_len = np.diff(np.concatenate((run_first, [nnz])))
+    run_group = group_id[run_first]
+    runs_per_group = np.bincount(run_group, minlength=n_groups)
+    run_first_of_group = np.concatenate(([0], np.cumsum(runs_per_group)[:-1]))
+    run_pos = np.arange(len(run_first)) - run_first_of_group[run_group]
+    assert runs_per_group.max(initial=0) <= GROUP_MAX_RUNS
+    hint = np.where(runs_per_group[run_group] == 1, 0,
+                    np.where(run_pos == 0, 1, np.where(run_pos == runs_per_group[run_group] - 1, 3, 2)))
+
+    groups_per_tile = np.bincount(tile_s[g_first], minlength=n_tiles)
+    tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
+    touched = np.zeros(n_tiles, dtype=np.int64)
+    np.bitwise_or.at(touched, tile, np.int64(1) << (outs - tile * T))
+
+    hdr_ints = 4 + 4 * n_tiles
+    grp_off = ceil_div(hdr_ints, GROUP_INTS) * GROUP_INTS
+    sched = np.zeros(grp_off + GROUP_INTS * n_groups, dtype=np.int32)
     sched[0:4] = (n_tiles, T, n_groups, nnz)
-    th = sched[hdr_off:grp_off].reshape(n_tiles, 4)
-    th[:, 0] = grp_off + 4 * tile_first_group
+    th = sched[4:hdr_ints].reshape(n_tiles, 4)
+    th[:, 0] = tile_first_group
     th[:, 1] = groups_per_tile
     th[:, 2] = np.arange(n_tiles) * T
-    th[:, 3] = np.minimum(T, n_out - np.arange(n_tiles) * T)
-    gr = sched[grp_off:pair_off].reshape(n_groups, 4)
+    th[:, 3] = np.minimum(T, n_out - np.arange(n_tiles) * T) | (touched << 8)
+    gr = sched[grp_off:].reshape(n_groups, GROUP_INTS)
     gr[:, 0] = ins_s[g_first]
-    gr[:, 1] = pair_off + 2 * g_first
-    gr[:, 2] = g_count
-    pr = sched[pair_off:].reshape(nnz, 2)
-    pr[:, 0] = outs_s - tile_s * T
-    pr[:, 1] = w_s
-    return sched
+    gr[:, 1] = g_count | (runs_per_group << 8)
+    gr[group_id, 4 + pos_in_group] = w_s
+    wbytes16 = (bsize * bsize * 2) >> 4
+    r0 = pos_in_group[run_first] * wbytes16 | ((slot_s[run_first] * bsize) << 16)
+    r1 = ((run_len * bsize) >> 3) | (accumulate[run_first] << 8) | (hint << 16)
+    gr[run_group, 12 + 2 * run_pos] = r0
+    gr[run_group, 13 + 2 * run_pos] = r1
+    return sched, grp_off
 
 
 # ---------------------------------------------------------------------------------------

@@ -14,7 +14,9 @@ from . import _lib
 from .lut import MatmulLuts
 
 # tcgen05 tile width (output blocks whose accumulators share one CTA's tensor memory)
-_TILE_BLOCKS = {32: 8, 64: 4}
+_TILE_BLOCKS = {32: 16, 64: 8}
+# W blocks per schedule group == W slots per pipeline stage of the kernel (csrc/tc.cuh XpropCfg::WPS)
+_W_PER_GROUP = {32: 8, 64: 4}
 
 
 def _as_2d(t, axis, feat):
@@ -111,10 +113,15 @@ class BlocksparseMatMul(object):
                 "bprop": torch.as_tensor(self._luts.bprop_rows, device=device),
                 "updat": torch.as_tensor(self.updat_lut, device=device),
             }
-            tb = _TILE_BLOCKS.get(self.bsize)
+            tb = _TILE_BLOCKS.get(self.bsize) if self.axis == 1 else None
             if tb:
-                d["fprop_sched"] = torch.as_tensor(self._luts.tile_schedule(False, tb), device=device)
-                d["bprop_sched"] = torch.as_tensor(self._luts.tile_schedule(True, tb), device=device)
+                wpg = _W_PER_GROUP[self.bsize]
+                fs, foff = self._luts.tile_schedule(False, tb, self.bsize, wpg)
+                bs_, boff = self._luts.tile_schedule(True, tb, self.bsize, wpg)
+                d["fprop_sched"] = torch.as_tensor(fs, device=device)
+                d["bprop_sched"] = torch.as_tensor(bs_, device=device)
+                d["sched_tiles_f"], d["sched_tiles_b"], d["tile_blocks"] = int(fs[0]), int(bs_[0]), tb
+                d["sched_off_f"], d["sched_off_b"] = foff, boff
             self._dev[key] = d
         return d
 
@@ -148,7 +155,8 @@ class BlocksparseMatMul(object):
                             lut.data_ptr(), n_out, n_in, self.blocks,
                             x2.data_ptr(), w.data_ptr(), y2.data_ptr(), N,
                             _lib.ptr(gate),
-                            _lib.ptr(sched), 0 if sched is None else sched.numel(),
+                            _lib.ptr(sched), d.get("sched_tiles_b" if bprop else "sched_tiles_f", 0), d.get("tile_blocks", 0),
+                            d.get("sched_off_b" if bprop else "sched_off_f", 0),
                             flags, _lib.stream_ptr())
         _lib.check(rc, "bsmm_xprop")
         if self.axis == 0:
@@ -190,7 +198,7 @@ class BlocksparseMatMul(object):
         rc = lib.bsmm_updat(_lib.dtype_code(x0.dtype), _lib.dtype_code(dw.dtype), self.axis, self.bsize,
                             d["updat"].data_ptr(), self.blocks, self.CB, self.KB,
                             xp, ep, len(xs2), dw.data_ptr(), N, float(alpha), beta,
-                            _lib.ptr(gate), int(bool(dw_gated)), None, 0, flags, _lib.stream_ptr())
+                            _lib.ptr(gate), int(bool(dw_gated)), None, 0, 0, 0, flags, _lib.stream_ptr())
         _lib.check(rc, "bsmm_updat")
         return dw
 

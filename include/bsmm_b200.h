@@ -73,6 +73,9 @@ int         bsmm_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* name of the kernel family the last successful call on this thread dispatched to
  * ("tcgen05_xprop_bs32", "fma_xprop", ...) -- used by tests to prove which path ran */
 const char* bsmm_last_kernel(void);
+/* Debug aid: synchronises the current device, then returns and clears the sticky device-side error
+ * word (non-zero if a tensor-core kernel's bounded barrier wait timed out since the last call). */
+int         bsmm_device_error(void);
 
 /* ---- block-sparse matmul -------------------------------------------------------- */
 
@@ -87,14 +90,16 @@ const char* bsmm_last_kernel(void);
  * lut: row LUT grouped by output block (n_out headers).  Output blocks with no entries are
  *    zero-filled (reference behaviour, cn_64.cu:243-253).
  * sched: optional tile schedule for the tcgen05 kernels built by the host layer
- *    (blocksparse_b200/lut.py:build_tile_schedule); NULL selects the CUDA-core kernels.
+ *    (blocksparse_b200/lut.py:build_tile_schedule, device memory) with its shape passed by value:
+ *    sched_tiles output tiles of sched_tile_blocks consecutive output blocks each, group records
+ *    starting at int32 index sched_groups_off; NULL selects the CUDA-core kernels.
  * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).
  */
 int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
                const int32_t* lut, int n_out, int n_in, int blocks,
                const void* x, const void* w, void* y, int N,
                const float* gate,
-               const int32_t* sched, int sched_len,
+               const int32_t* sched, int sched_tiles, int sched_tile_blocks, int sched_groups_off,
                int flags, void* stream);
 
 /*
@@ -112,7 +117,7 @@ int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
                const void* const* xs, const void* const* dys, int pcount,
                void* dw, int N, float alpha, float beta,
                const float* gate, int gated_dw,
-               const int32_t* sched, int sched_len,
+               const int32_t* sched, int sched_tiles, int sched_tile_blocks, int sched_groups_off,
                int flags, void* stream);
 
 /* dg[w] = sum_ij dw[w][i][j] * w[w][i][j]   (BlocksparseMatmulDG, op.cc:490-540) */

@@ -71,7 +71,7 @@ def _decode_rows(rows, n_out):
     return out
 
 
-def test_row_lut_and_tile_schedule_cover_every_block_once():
+def test_row_lut_matches_lists():
     for lay in _random_layouts():
         L = MatmulLuts(lay)
         for bprop in (False, True):
@@ -81,25 +81,56 @@ def test_row_lut_and_tile_schedule_cover_every_block_once():
             dec = _decode_rows(rows, n_out)
             for o in range(n_out):
                 assert dec[o] == lists[o]
-            for T in (4, 8, 16):
-                s = L.tile_schedule(bprop, T)
-                n_tiles, Tt, n_groups, n_pairs = s[:4]
-                assert Tt == T and n_pairs == L.blocks and n_tiles == -(-n_out // T)
-                seen = set()
-                for t in range(n_tiles):
-                    fg, ng, fo, no = s[4 + 4 * t: 8 + 4 * t]
-                    assert fo == t * T and no == min(T, n_out - fo)
-                    prev_in = -1
-                    for gi in range(ng):
-                        ib, fp, npair, _ = s[fg + 4 * gi: fg + 4 * gi + 4]
-                        assert ib > prev_in and npair >= 1
-                        prev_in = ib
-                        for pi in range(npair):
-                            slot, w = s[fp + 2 * pi: fp + 2 * pi + 2]
-                            assert 0 <= slot < no
-                            assert (int(ib), int(w)) in lists[fo + slot]
-                            seen.add(int(w))
-                assert len(seen) == L.blocks
+
+
+@pytest.mark.parametrize("bsize,T,wpg", [(32, 16, 8), (32, 15, 8), (32, 4, 3), (64, 8, 4)])
+def test_tile_schedule_is_a_faithful_regrouping(bsize, T, wpg):
+    """Simulate the device loops on the schedule: every LUT entry is issued exactly once, on the right
+    accumulator, with accumulate == 0 exactly for the first touch of each accumulator in its tile."""
+    for lay in _random_layouts():
+        L = MatmulLuts(lay)
+        for bprop in (False, True):
+            lists = dict(L.bprop_list if bprop else L.fprop_list)
+            n_out = L.CB if bprop else L.KB
+            s, off = L.tile_schedule(bprop, T, bsize, wpg)
+            n_tiles, Tt, n_groups, n_w_total = s[:4]
+            assert Tt == T and n_w_total == L.blocks and n_tiles == -(-n_out // T) and off % 32 == 0
+            wbytes16 = (bsize * bsize * 2) >> 4
+            seen = set()
+            gi_expected = 0
+            for t in range(n_tiles):
+                fg, ng, fo, packed = s[4 + 4 * t: 8 + 4 * t]
+                no, mask = packed & 0xff, packed >> 8
+                assert fg == gi_expected and fo == t * T and no == min(T, n_out - fo)
+                assert mask == sum(1 << sl for sl in range(no) if lists[fo + sl])
+                gi_expected += ng
+                touched = set()
+                prev_in = -1
+                for g in range(fg, fg + ng):
+                    rec = s[off + 32 * g: off + 32 * g + 32]
+                    ib, n_w, n_runs = rec[0], rec[1] & 0xff, rec[1] >> 8
+                    assert 1 <= n_w <= wpg and 1 <= n_runs <= n_w and ib >= prev_in
+                    prev_in = ib
+                    covered = 0
+                    for r in range(n_runs):
+                        r0, r1 = int(rec[12 + 2 * r]), int(rec[13 + 2 * r])
+                        w_slot, col = (r0 & 0xffff) // wbytes16, r0 >> 16
+                        n, acc, hint = (r1 & 0xff) << 3, (r1 >> 8) & 1, r1 >> 16
+                        assert (r0 & 0xffff) % wbytes16 == 0 and col % bsize == 0 and n % bsize == 0 and n <= 256
+                        assert w_slot == covered          # runs tile the staged W blocks in order
+                        assert hint == (0 if n_runs == 1 else 1 if r == 0 else 3 if r == n_runs - 1 else 2)
+                        for i in range(n // bsize):
+                            slot = col // bsize + i
+                            w = int(rec[4 + w_slot + i])
+                            assert 0 <= slot < no and (int(ib), w) in lists[fo + slot]
+                            assert acc == (1 if slot in touched else 0)
+                            assert w not in seen
+                            seen.add(w)
+                        for i in range(n // bsize):
+                            touched.add(col // bsize + i)
+                        covered += n // bsize
+                    assert covered == n_w
+            assert len(seen) == L.blocks and gi_expected == n_groups
 
 
 def _cb(name, has_mask):

@@ -1,0 +1,76 @@
+"""GPU parity of the tcgen05 kernel families (forced with BSMM_FLAG_FORCE_TC so a silent fall-back to the
+CUDA-core kernels cannot pass) against the oracle, at sizes the NumPy loops finish in seconds."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import ref_errors
+from blocksparse_b200 import BlocksparseMatMul, _lib
+from oracle.bsmm_oracle import MatmulOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def layout(rng, CB, KB, density, empty_col=None, empty_row=None):
+    lay = (rng.random((CB, KB)) < density).astype(np.int32)
+    lay[rng.integers(CB), rng.integers(KB)] = 1
+    if empty_col is not None:
+        lay[:, empty_col] = 0
+    if empty_row is not None:
+        lay[empty_row, :] = 0
+    if lay.sum() == 0:
+        lay[0, 0] = 1
+    return lay
+
+
+CASES = [
+    # CB, KB, density, N, bs
+    (8, 8, 0.3, 128, 32),
+    (5, 37, 0.5, 200, 32),        # ragged N, more than two output tiles (16 blocks each), rectangular
+    (40, 33, 0.08, 1, 32),        # single row
+    (20, 20, 1.0, 257, 32),       # dense layout: 16 pairs per group
+    (64, 64, 0.2, 640, 32),       # many tiles per CTA
+    (6, 9, 0.5, 130, 64),
+    (16, 17, 0.3, 64, 64),
+    (12, 12, 1.0, 300, 64),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", CASES)
+def test_tc_xprop_matches_oracle(case, dtype):
+    CB, KB, density, N, bs = case
+    rng = np.random.default_rng(CB * 1000 + KB * 10 + N)
+    lay = layout(rng, CB, KB, density, empty_col=KB // 2 if density < 1 else None, empty_row=1 if density < 1 and CB > 2 else None)
+    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=1)
+    orc = MatmulOracle(lay, bs, 1)
+    W = torch.as_tensor(rng.normal(0, 0.1, bsmm.w_shape).astype(np.float32)).to(dtype)
+    X = torch.as_tensor(rng.normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).to(dtype)
+    E = torch.as_tensor(rng.normal(0, 1, bsmm.o_shape(N)).astype(np.float32)).to(dtype)
+    Wn, Xn, En = W.float().numpy(), X.float().numpy(), E.float().numpy()
+    for name, got_fn, ref in [("fprop", lambda: bsmm.fprop(X.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_TC), orc.fprop_dense(Xn, Wn)),
+                              ("bprop", lambda: bsmm.bprop(E.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_TC), orc.bprop_dense(En, Wn))]:
+        got = got_fn()
+        assert _lib.device_error() == 0, "a tcgen05 kernel hit its bounded-wait timeout"
+        assert _lib.last_kernel().startswith("tcgen05_xprop"), _lib.last_kernel()
+        mx, l2 = ref_errors(got.float().cpu().numpy(), ref)
+        assert l2 <= (4e-3 if dtype == torch.bfloat16 else 1e-3), "%s l2 %.3e max %.3e" % (name, l2, mx)
+        assert mx <= (4e-2 if dtype == torch.bfloat16 else 1e-2), "%s l2 %.3e max %.3e" % (name, l2, mx)
+        # agrees with the fp32-accumulating CUDA-core path up to one output rounding
+        gen = bsmm.fprop(X.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_GENERIC) if name == "fprop" else \
+            bsmm.bprop(E.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_GENERIC)
+        diff = (got.float() - gen.float()).abs().max().item()
+        scale = gen.float().abs().max().item()
+        assert diff <= scale * 2.0 ** -7, "tcgen05 vs FMA path differ by %g (scale %g)" % (diff, scale)
+
+
+def test_tc_xprop_repeatable_and_stream_ordered():
+    rng = np.random.default_rng(3)
+    lay = layout(rng, 32, 32, 0.25)
+    bsmm = BlocksparseMatMul(lay, block_size=32, feature_axis=1)
+    W = (torch.randn(bsmm.w_shape, device="cuda") * 0.1).bfloat16()
+    X = torch.randn(bsmm.i_shape(1024), device="cuda").bfloat16()
+    y0 = bsmm.fprop(X, W, flags=_lib.FLAG_FORCE_TC)
+    for _ in range(5):
+        y = bsmm.fprop(X, W, flags=_lib.FLAG_FORCE_TC)
+        assert torch.equal(y, y0)          # no atomics, no races: bit-identical run to run
