@@ -101,7 +101,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   uint8_t* sStage = smem;                         // XS x (activation tile | WPS W blocks)
   uint8_t* sO = smem + XS * STAGE_BYTES;          // STG x XBYTES staging for the output tile
   __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty;
-  __shared__ int2 cmd[XS][8];                     // run commands of the group in each stage
+  __shared__ __align__(16) int4 cmd[XS][8];       // per run: (B descriptor low word for K slice 0, D tmem address, idesc, accumulate)
   __shared__ int cmd_n[XS];                       // number of runs
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
@@ -131,6 +131,8 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     // gc % XPROP_PRODUCERS == warp; lane i holds int i of the group record.
     uint32_t gbase = 0;                   // groups of earlier tiles
     bool alive = true;
+    const uint32_t p_idesc0 = ptx::make_idesc_f16(BF16, false, !p.bprop, 128, 0);
+    const uint32_t p_bdesc_lo = (uint32_t)ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
       const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
       const int32_t* th = sched + 4 + 4 * kt;
@@ -149,7 +151,14 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         const int counts = __shfl_sync(0xffffffffu, cur, 1);
         const int n_w = counts & 0xff, n_runs = counts >> 8;
         if (!__all_sync(0xffffffffu, ptx::mbar_wait(&empty[st], ((gc / XS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
-        if (lane >= 12 && lane < 12 + 2 * n_runs) reinterpret_cast<int*>(&cmd[st][0])[lane - 12] = cur;
+        // lanes 12..19 hold int0 of run (lane-12); int1 sits 8 lanes up.  They write the ready-to-issue
+        // command so the issuing thread only moves registers.
+        const uint32_t r1 = (uint32_t)__shfl_down_sync(0xffffffffu, cur, 8);
+        if (lane >= 12 && lane < 12 + n_runs) {
+          const uint32_t r0 = (uint32_t)cur;
+          cmd[st][lane - 12] = make_int4((int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (r0 & 0xffffu)),
+                                         (int)(tmem + (r0 >> 16)), (int)(p_idesc0 | (r1 & ~1u)), (int)(r1 & 1u));
+        }
         if (lane == 0) cmd_n[st] = n_runs;
         __syncwarp();
         uint8_t* stage = sStage + st * STAGE_BYTES;
@@ -165,12 +174,11 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     }
   } else if (warp == XPROP_PRODUCERS) {
     // ================================ MMA issuer ================================
-    const uint32_t idesc0 = ptx::make_idesc_f16(BF16, false, !p.bprop, 128, 0);
     // fprop: B = W[c][k] read as K x N with N contiguous (MN-major): K=16 slice = 16 rows, blocks LBO apart.
     // bprop: B = W[c][k] read as N x K with K contiguous (K-major):  K=16 slice = 32 bytes along the row.
     const uint32_t b_kstep16 = (p.bprop ? 32u : 16u * ROW) >> 4;
     const uint64_t a_desc0 = ptx::make_smem_desc(ptx::smem_u32(sStage), 16, Cfg::SBO, Cfg::SWZ);
-    const uint64_t b_desc0 = ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
+    const uint32_t b_desc_hi = (uint32_t)(ptx::make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) >> 32);
     uint32_t gc = 0, tile_it = 0;
     bool alive = true;
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x, ++tile_it) {
@@ -185,22 +193,22 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         const int n_runs = cmd_n[st];
         if (ptx::elect_one()) {
           const uint64_t a_st = a_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
-          const uint64_t b_st = b_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
+          // all run commands of the group in registers first (independent LDS.128s), then straight-line
+          // issue: run 0 fills the A collector, runs 1.. reuse it
+          int4 c[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) c[r] = cmd[st][r];
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
             const uint64_t adesc = a_st + (uint64_t)(ks * 2);
-#pragma unroll 1
-            for (int r = 0; r < n_runs; ++r) {
-              const int2 c = cmd[st][r];
-              const uint64_t bdesc = b_st + (uint64_t)(((uint32_t)c.x & 0xffffu) + ks * b_kstep16);
-              const uint32_t d = tmem + ((uint32_t)c.x >> 16);
-              const uint32_t idesc = idesc0 | (((uint32_t)c.y & 0xffu) << 17);
-              const uint32_t acc = (ks > 0) ? 1u : (((uint32_t)c.y >> 8) & 1u);
-              const uint32_t hint = (uint32_t)c.y >> 16;
-              if (hint == 0)      ptx::mma_ss(d, adesc, bdesc, idesc, acc);
-              else if (hint == 1) ptx::mma_ss_a_fill(d, adesc, bdesc, idesc, acc);
-              else if (hint == 2) ptx::mma_ss_a_use(d, adesc, bdesc, idesc, acc);
-              else                ptx::mma_ss_a_lastuse(d, adesc, bdesc, idesc, acc);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (r < n_runs) {
+                const uint64_t bdesc = ((uint64_t)b_desc_hi << 32) | (uint32_t)((uint32_t)c[r].x + ks * b_kstep16);
+                const uint32_t acc = (ks > 0) ? 1u : (uint32_t)c[r].w;
+                if (r == 0) ptx::mma_ss_a_fill((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
+                else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
+              }
             }
           }
           ptx::tc_commit(&empty[st]);       // the stage is free once these MMAs retire

@@ -188,7 +188,7 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
         (N = run_len*bsize); a dense layout degenerates to ordinary wide GEMM instructions;
       * the accumulate flag of every run (0 = first touch of those accumulators in this tile) -- runs
         are split where the flag changes;
-      * the A-collector hint of every run (0 plain, 1 fill, 2 use, 3 last use).
+      * (the A-collector hint needs no field: the first run of a group fills the collector, the rest reuse it).
 
     int32 layout:
       [0] n_tiles  [1] blocks_per_tile  [2] total groups  [3] total W loads
@@ -197,9 +197,8 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
       group records [groups][32]:
           [0] in_block   [1] n_w | n_runs << 8   [2..3] reserved
           [4..11]  W block ids, in staging-slot order
-          [12..27] runs, two ints each:
-                   int0 = (w_slot * bsize*bsize*2) >> 4  |  (accumulator column << 16)
-                   int1 = (N >> 3) | accumulate << 8 | collector_hint << 16
+          [12..19] run r, int0 = (w_slot * bsize*bsize*2) >> 4  |  (accumulator column << 16)
+          [20..27] run r, int1 = (N >> 3) << 17 | accumulate     (N pre-shifted to its instruction-descriptor field)
     Returns (schedule, groups_offset): groups_offset is the int32 index of the first group record.
     """
     T = int(blocks_per_tile)
@@ -245,8 +244,6 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     run_first_of_group = np.concatenate(([0], np.cumsum(runs_per_group)[:-1]))
     run_pos = np.arange(len(run_first)) - run_first_of_group[run_group]
     assert runs_per_group.max(initial=0) <= GROUP_MAX_RUNS
-    hint = np.where(runs_per_group[run_group] == 1, 0,
-                    np.where(run_pos == 0, 1, np.where(run_pos == runs_per_group[run_group] - 1, 3, 2)))
 
     groups_per_tile = np.bincount(tile_s[g_first], minlength=n_tiles)
     tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
@@ -268,9 +265,9 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     gr[group_id, 4 + pos_in_group] = w_s
     wbytes16 = (bsize * bsize * 2) >> 4
     r0 = pos_in_group[run_first] * wbytes16 | ((slot_s[run_first] * bsize) << 16)
-    r1 = ((run_len * bsize) >> 3) | (accumulate[run_first] << 8) | (hint << 16)
-    gr[run_group, 12 + 2 * run_pos] = r0
-    gr[run_group, 13 + 2 * run_pos] = r1
+    r1 = (((run_len * bsize) >> 3) << 17) | accumulate[run_first]
+    gr[run_group, 12 + run_pos] = r0
+    gr[run_group, 20 + run_pos] = r1
     return sched, grp_off
 
 

@@ -113,12 +113,11 @@ def test_tile_schedule_is_a_faithful_regrouping(bsize, T, wpg):
                     prev_in = ib
                     covered = 0
                     for r in range(n_runs):
-                        r0, r1 = int(rec[12 + 2 * r]), int(rec[13 + 2 * r])
+                        r0, r1 = int(rec[12 + r]), int(rec[20 + r])
                         w_slot, col = (r0 & 0xffff) // wbytes16, r0 >> 16
-                        n, acc, hint = (r1 & 0xff) << 3, (r1 >> 8) & 1, r1 >> 16
+                        n, acc = (r1 >> 17) << 3, r1 & 1
                         assert (r0 & 0xffff) % wbytes16 == 0 and col % bsize == 0 and n % bsize == 0 and n <= 256
                         assert w_slot == covered          # runs tile the staged W blocks in order
-                        assert hint == (0 if n_runs == 1 else 1 if r == 0 else 3 if r == n_runs - 1 else 2)
                         for i in range(n // bsize):
                             slot = col // bsize + i
                             w = int(rec[4 + w_slot + i])
