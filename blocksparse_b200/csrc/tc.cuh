@@ -203,12 +203,11 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             const uint64_t adesc = a_st + (uint64_t)(ks * 2);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              if (r < n_runs) {
-                const uint64_t bdesc = ((uint64_t)b_desc_hi << 32) | (uint32_t)((uint32_t)c[r].x + ks * b_kstep16);
-                const uint32_t acc = (ks > 0) ? 1u : (uint32_t)c[r].w;
-                if (r == 0) ptx::mma_ss_a_fill((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
-                else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
-              }
+              if (r >= n_runs) break;              // a real (uniform) branch: skipped runs cost nothing
+              const uint64_t bdesc = ((uint64_t)b_desc_hi << 32) | (uint32_t)((uint32_t)c[r].x + ks * b_kstep16);
+              const uint32_t acc = (ks > 0) ? 1u : (uint32_t)c[r].w;
+              if (r == 0) ptx::mma_ss_a_fill((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
+              else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
             }
           }
           ptx::tc_commit(&empty[st]);       // the stage is free once these MMAs retire
@@ -348,10 +347,10 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
                             : launch_tc_xprop<64, false>(p, maps, dev.sm_count, s);
 }
 
-inline int tc_updat(int, int, int, int, const int32_t*, int, int, int, const void* const*, const void* const*, int,
-                    void*, int, float, float, const float*, int, const int32_t*, int, int, int, cudaStream_t) { return TC_NOT_APPLICABLE; }
 inline int tc_bst_nt(int, int, int, const int32_t*, int, int, const void*, const void*, void*, int, int, int, int, int,
                      cudaStream_t) { return TC_NOT_APPLICABLE; }
 inline int tc_bst_xn(int, int, int, int, const int32_t*, int, int, int, const void*, const void*, void*, int, int, int,
                      int, int, cudaStream_t) { return TC_NOT_APPLICABLE; }
 }  // namespace bsmm
+
+#include "tc_updat.cuh"

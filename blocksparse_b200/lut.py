@@ -163,6 +163,9 @@ class MatmulLuts(object):
         self.bprop_rows, self.bprop_max = row_lut(b[0], b[1], b[2], CB)
         self._f, self._b = f, b
 
+    def updat_schedule(self, bsize, k_per_tile=None):
+        return build_updat_schedule(self.updat_lut, self.CB, self.KB, bsize, k_per_tile)
+
     def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8):
         outs, ins, wids = self._b if bprop else self._f
         n_out = self.CB if bprop else self.KB
@@ -269,6 +272,69 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     gr[run_group, 12 + run_pos] = r0
     gr[run_group, 20 + run_pos] = r1
     return sched, grp_off
+
+
+UPDAT_REC_INTS = 64      # one 256-byte record per updat tile
+
+
+def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None):
+    """Schedule for the tcgen05 updat kernel (csrc/tc_updat.cuh): a "gathered dense GEMM".
+
+    A tile pairs a GROUP of 128/bsize consecutive input blocks (128 features = the MMA M axis) with up
+    to `k_per_tile` output blocks taken from a window of consecutive output blocks, keeping only those
+    that have at least one active block in the group.  The kept output blocks are compacted side by
+    side (shared-memory slots and accumulator columns s = 0..n_act-1), so each K step of the reduction
+    over the minibatch is ONE MMA of N = n_act*bsize columns, and output blocks with nothing to update
+    are neither loaded nor multiplied.
+
+    int32 layout:
+      [0] n_tiles  [1] blocks per group  [2] k_per_tile  [3] UPDAT_REC_INTS
+      tile records [n_tiles][64], sorted by decreasing n_act (longest first for load balance):
+          [0] first input block of the group   [1] n_act
+          [8  .. 8+k_per_tile)            output block id of compact slot s
+          [16 + i*k_per_tile + s]         W block id for (input block i of the group, slot s) or -1
+    Returns (schedule, first_record_offset).
+    """
+    G = 128 // bsize
+    if k_per_tile is None:
+        k_per_tile = 256 // bsize
+    KT = int(k_per_tile)
+    assert KT * bsize <= 256 and 16 + G * KT <= UPDAT_REC_INTS
+    lut = np.asarray(updat_lut, dtype=np.int64).reshape(-1, 2)
+    cs, ks = lut[:, 0], lut[:, 1]
+    wid = np.arange(len(cs), dtype=np.int64)
+    grp, win = cs // G, ks // KT
+    n_win = ceil_div(KB, KT)
+    tile_key = grp * n_win + win
+    # distinct (tile, k) pairs -> compact slot numbers
+    tk = tile_key * KB + ks
+    uniq_tk, inv = np.unique(tk, return_inverse=True)
+    u_tile = uniq_tk // KB
+    u_k = uniq_tk % KB
+    new_tile = np.ones(len(uniq_tk), dtype=bool)
+    new_tile[1:] = u_tile[1:] != u_tile[:-1]
+    tile_start = np.nonzero(new_tile)[0]
+    tile_idx_of_u = np.cumsum(new_tile) - 1
+    slot_of_u = np.arange(len(uniq_tk)) - tile_start[tile_idx_of_u]
+    n_tiles = len(tile_start)
+    n_act = np.diff(np.concatenate((tile_start, [len(uniq_tk)])))
+    order = np.argsort(-n_act, kind="stable")            # longest tiles first
+    rank = np.empty(n_tiles, dtype=np.int64)
+    rank[order] = np.arange(n_tiles)
+
+    off = 4
+    sched = np.full(off + UPDAT_REC_INTS * n_tiles, -1, dtype=np.int32)
+    sched[0:4] = (n_tiles, G, KT, UPDAT_REC_INTS)
+    rec = sched[off:].reshape(n_tiles, UPDAT_REC_INTS)
+    rec[:, 0:8] = 0
+    t_of_u = rank[tile_idx_of_u]
+    rec[t_of_u, 0] = (u_tile // n_win) * G
+    rec[rank, 1] = n_act
+    rec[t_of_u, 8 + slot_of_u] = u_k
+    # blocks
+    t_of_blk = rank[tile_idx_of_u[inv]]
+    rec[t_of_blk, 16 + (cs % G) * KT + slot_of_u[inv]] = wid
+    return sched, off
 
 
 # ---------------------------------------------------------------------------------------

@@ -122,6 +122,9 @@ class BlocksparseMatMul(object):
                 d["bprop_sched"] = torch.as_tensor(bs_, device=device)
                 d["sched_tiles_f"], d["sched_tiles_b"], d["tile_blocks"] = int(fs[0]), int(bs_[0]), tb
                 d["sched_off_f"], d["sched_off_b"] = foff, boff
+                us, uoff = self._luts.updat_schedule(self.bsize)
+                d["updat_sched"] = torch.as_tensor(us, device=device)
+                d["updat_tiles"], d["updat_kt"] = int(us[0]), int(us[2])
             self._dev[key] = d
         return d
 
@@ -198,7 +201,9 @@ class BlocksparseMatMul(object):
         rc = lib.bsmm_updat(_lib.dtype_code(x0.dtype), _lib.dtype_code(dw.dtype), self.axis, self.bsize,
                             d["updat"].data_ptr(), self.blocks, self.CB, self.KB,
                             xp, ep, len(xs2), dw.data_ptr(), N, float(alpha), beta,
-                            _lib.ptr(gate), int(bool(dw_gated)), None, 0, 0, 0, flags, _lib.stream_ptr())
+                            _lib.ptr(gate), int(bool(dw_gated)),
+                            _lib.ptr(d.get("updat_sched")), d.get("updat_tiles", 0), d.get("updat_kt", 0), 0,
+                            flags, _lib.stream_ptr())
         _lib.check(rc, "bsmm_updat")
         return dw
 

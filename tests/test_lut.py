@@ -171,3 +171,32 @@ def test_classes_construct_and_pickle_without_gpu():
     assert t.blocks == 6 and t.nn_max == 3 and t.block_coord(1) == (1, 0)
     t2 = pickle.loads(pickle.dumps(t))
     np.testing.assert_array_equal(t2.softmax_mask_np, t.softmax_mask_np)
+
+
+@pytest.mark.parametrize("bsize", [32, 64])
+def test_updat_schedule_covers_every_block_once(bsize):
+    for lay in _random_layouts():
+        L = MatmulLuts(lay)
+        s, off = L.updat_schedule(bsize)
+        n_tiles, G, KT, stride = s[:4]
+        assert G == 128 // bsize and KT == 256 // bsize and stride == 64 and off == 4
+        rec = s[off:].reshape(n_tiles, 64)
+        seen = set()
+        assert (np.diff(rec[:, 1]) <= 0).all()            # longest tiles first
+        for t in range(n_tiles):
+            c0, n_act = rec[t, 0], rec[t, 1]
+            assert c0 % G == 0 and 1 <= n_act <= KT
+            ks = rec[t, 8:8 + n_act]
+            assert len(set(ks.tolist())) == n_act and (ks // KT == ks[0] // KT).all()
+            for sl in range(n_act):
+                col_has_block = False
+                for i in range(G):
+                    w = rec[t, 16 + i * KT + sl]
+                    if w >= 0:
+                        assert tuple(L.updat_lut[w]) == (c0 + i, ks[sl]) and w not in seen
+                        seen.add(int(w))
+                        col_has_block = True
+                assert col_has_block                       # compacted: no slot without work
+            for sl in range(n_act, KT):
+                assert (rec[t, [16 + i * KT + sl for i in range(G)]] == -1).all()
+        assert len(seen) == L.blocks

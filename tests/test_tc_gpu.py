@@ -74,3 +74,52 @@ def test_tc_xprop_repeatable_and_stream_ordered():
     for _ in range(5):
         y = bsmm.fprop(X, W, flags=_lib.FLAG_FORCE_TC)
         assert torch.equal(y, y0)          # no atomics, no races: bit-identical run to run
+
+
+UPDAT_CASES = [
+    # CB, KB, density, N, bs, pairs
+    (8, 8, 0.3, 128, 32, 1),
+    (5, 37, 0.5, 200, 32, 2),      # group of 4 input blocks is ragged (5 = 4 + 1), N not a multiple of 64
+    (40, 33, 0.08, 1, 32, 1),
+    (20, 20, 1.0, 257, 32, 3),
+    (64, 64, 0.2, 640, 32, 8),     # 8 (x, dy) pairs in one launch
+    (6, 9, 0.5, 130, 64, 1),
+    (16, 17, 0.3, 64, 64, 2),
+    (12, 12, 1.0, 300, 64, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", UPDAT_CASES)
+def test_tc_updat_matches_oracle(case, dtype):
+    CB, KB, density, N, bs, pairs = case
+    rng = np.random.default_rng(CB * 1000 + KB * 10 + N + 7)
+    lay = layout(rng, CB, KB, density, empty_col=KB // 2 if density < 1 else None, empty_row=1 if density < 1 and CB > 2 else None)
+    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=1)
+    orc = MatmulOracle(lay, bs, 1)
+    xs, es, ref = [], [], np.zeros(bsmm.w_shape)
+    for _ in range(pairs):
+        X = torch.as_tensor(rng.normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).to(dtype)
+        E = torch.as_tensor(rng.normal(0, 1, bsmm.o_shape(N)).astype(np.float32)).to(dtype)
+        xs.append(X.cuda()); es.append(E.cuda())
+        ref += orc.updat_dense(X.float().numpy(), E.float().numpy())
+    # fp32 output: only the 16-bit INPUT rounding separates us from the oracle (which sees the same rounded inputs)
+    dw32 = bsmm.updat(xs, es, dw_dtype=torch.float32, flags=_lib.FLAG_FORCE_TC)
+    assert _lib.device_error() == 0, "a tcgen05 kernel hit its bounded-wait timeout"
+    assert _lib.last_kernel().startswith("tcgen05_updat"), _lib.last_kernel()
+    mx, l2 = ref_errors(dw32.cpu().numpy(), ref)
+    assert l2 <= 1e-5 and mx <= 1e-4, "fp32-out updat l2 %.3e max %.3e" % (l2, mx)
+    # native-dtype output, alpha, and in-place accumulation (beta = 1)
+    dw = bsmm.updat(xs, es, alpha=0.5, flags=_lib.FLAG_FORCE_TC)
+    mx, l2 = ref_errors(dw.float().cpu().numpy(), 0.5 * ref)
+    assert l2 <= (4e-3 if dtype == torch.bfloat16 else 1e-3), "updat l2 %.3e max %.3e" % (l2, mx)
+    acc = dw32.clone()
+    bsmm.updat(xs[:1], es[:1], dw=acc, flags=_lib.FLAG_FORCE_TC)
+    ref2 = ref + orc.updat_dense(xs[0].float().cpu().numpy(), es[0].float().cpu().numpy())
+    mx, l2 = ref_errors(acc.cpu().numpy(), ref2)
+    assert l2 <= 1e-5, "accumulate l2 %.3e" % l2
+    gate = torch.as_tensor((rng.random(bsmm.blocks) < 0.7).astype(np.float32) * 1.5).cuda()
+    dwg = bsmm.updat(xs, es, gate=gate, dw_gated=True, dw_dtype=torch.float32, flags=_lib.FLAG_FORCE_TC)
+    mx, l2 = ref_errors(dwg.cpu().numpy(), ref * gate.cpu().numpy()[:, None, None])
+    assert l2 <= 1e-5, "gated l2 %.3e" % l2
+    assert _lib.device_error() == 0
