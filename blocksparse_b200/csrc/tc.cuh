@@ -63,14 +63,28 @@ inline int make_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t in
 //   producer warps (2, alternating groups): one coalesced 128-byte load per group, prefetched a group
 //     ahead; lanes 4..11 each issue one W TMA load; lanes 12..27 copy the run commands to smem
 //   MMA warp: one barrier wait per group, then one LDS.64 + one tcgen05.mma per run and K slice
-template <int BS> struct XpropCfg;
-template <> struct XpropCfg<32> {
-  static constexpr int XS = 6, WPS = 8, STG = 8;               // group stages, W slots per stage, staging buffers
+// OCC = CTAs per SM.  OCC 2 halves the output tile (256 TMEM columns, 8/4 blocks) so that two CTAs --
+// two independent MMA-issuing threads -- share one SM's tensor core: the issue rate of one thread
+// (~45 cycles per N=32 MMA, profiles/r1_xprop_v3_ncu.txt) is what bounds the single-CTA kernel.
+template <int BS, int OCC> struct XpropCfg;
+template <> struct XpropCfg<32, 1> {
+  static constexpr int XS = 6, WPS = 8, STG = 8, TCOLS = 512;  // group stages, W slots per stage, staging buffers, TMEM columns
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;     // 64-byte rows
 };
-template <> struct XpropCfg<64> {
-  static constexpr int XS = 3, WPS = 4, STG = 4;
+// STG == 0 selects a direct epilogue (rows stored straight from registers, no staging).  Measured on B200
+// (profiles/r1_xprop_tuning.txt): XS=6/WPS=4/STG=0 is ~7 % SLOWER at 25 % density and 23 % slower at 100 % than
+// XS=3/WPS=8/STG=4, so the staged TMA-store epilogue stays.
+template <> struct XpropCfg<32, 2> {
+  static constexpr int XS = 3, WPS = 8, STG = 4, TCOLS = 256;
+  static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
+};
+template <> struct XpropCfg<64, 1> {
+  static constexpr int XS = 3, WPS = 4, STG = 4, TCOLS = 512;
   static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;   // 128-byte rows
+};
+template <> struct XpropCfg<64, 2> {
+  static constexpr int XS = 2, WPS = 2, STG = 2, TCOLS = 256;
+  static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;
 };
 constexpr int XPROP_PRODUCERS = 2;
 constexpr int XPROP_THREADS = (XPROP_PRODUCERS + 1 + 4) * 32;
@@ -84,13 +98,16 @@ struct XpropTcParams {
   int n_ktiles;              // output tiles along the feature axis
   int n_ntiles;              // ceil(N / 128)
   int bprop;
+  void* y;                   // output base, row pitch and row count (direct-store epilogue)
+  long long y_pitch;         // elements
+  int N;
 };
 struct XpropTmaps { CUtensorMap x, w, y; };
 
-template <int BS, bool BF16>
-__global__ void __launch_bounds__(XPROP_THREADS, 1)
+template <int BS, bool BF16, int OCC>
+__global__ void __launch_bounds__(XPROP_THREADS, OCC)
 tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) {
-  using Cfg = XpropCfg<BS>;
+  using Cfg = XpropCfg<BS, OCC>;
   constexpr int XS = Cfg::XS, WPS = Cfg::WPS, STG = Cfg::STG;
   constexpr int KS = BS / 16;                     // K=16 slices per block
   constexpr uint32_t XBYTES = 128 * BS * 2, WBYTES = BS * BS * 2;
@@ -119,7 +136,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&maps.x); ptx::prefetch_tensormap(&maps.w); ptx::prefetch_tensormap(&maps.y);
   }
-  if (warp == XPROP_PRODUCERS) { ptx::tmem_alloc(&tmem_base_s, 512); ptx::tmem_relinquish(); }
+  if (warp == XPROP_PRODUCERS) { ptx::tmem_alloc(&tmem_base_s, Cfg::TCOLS); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -233,6 +250,40 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*abort_flag) { g_tc_error = 6; break; }       // uniform across the 128 epilogue threads
       ptx::tc_fence_after();
+      if constexpr (STG == 0) {
+        // direct epilogue: thread = one row of the tile; BS 16-bit outputs = one contiguous row segment per block
+        const long long grow = (long long)nt * 128 + row;
+        uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + grow * p.y_pitch + (long long)first_out * BS;
+        for (int slot = 0; slot < n_out; ++slot) {
+#pragma unroll
+          for (int h = 0; h < BS / 32; ++h) {
+            uint32_t v[32];
+            if ((mask >> slot) & 1u) {
+              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
+              ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            if (grow < p.N) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = __uint_as_float(v[c * 8 + 2 * e]), b = __uint_as_float(v[c * 8 + 2 * e + 1]);
+                  if (BF16) { __nv_bfloat162 q = __floats2bfloat162_rn(a, b); pk[e] = *reinterpret_cast<uint32_t*>(&q); }
+                  else      { __half2 q = __floats2half2_rn(a, b);           pk[e] = *reinterpret_cast<uint32_t*>(&q); }
+                }
+                *reinterpret_cast<uint4*>(yrow + slot * BS + h * 32 + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) ptx::mbar_arrive(&acc_empty);
+      } else {
       for (int s0 = 0; s0 < n_out; s0 += STG) {
         // the staging buffers must have been drained by the TMA stores issued before
         if (etid == 0) ptx::tma_store_wait_read<0>();
@@ -275,24 +326,25 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
           ptx::tma_store_commit();
         }
       }
+      }
     }
     if (etid == 0) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == XPROP_PRODUCERS) ptx::tmem_dealloc(tmem, 512);
+  if (warp == XPROP_PRODUCERS) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int BS>
+template <int BS, int OCC>
 constexpr size_t xprop_smem_bytes() {
-  using Cfg = XpropCfg<BS>;
+  using Cfg = XpropCfg<BS, OCC>;
   return (size_t)Cfg::XS * (128 * BS * 2 + Cfg::WPS * BS * BS * 2) + (size_t)Cfg::STG * 128 * BS * 2;
 }
 
-template <int BS, bool BF16>
+template <int BS, bool BF16, int OCC>
 int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count, cudaStream_t s) {
-  auto kern = tc_xprop_kernel<BS, BF16>;
-  constexpr size_t smem = xprop_smem_bytes<BS>();
+  auto kern = tc_xprop_kernel<BS, BF16, OCC>;
+  constexpr size_t smem = xprop_smem_bytes<BS, OCC>();
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -300,7 +352,7 @@ int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count
     configured = true;
   }
   const int total = p.n_ktiles * p.n_ntiles;
-  const int grid = total < sm_count ? total : sm_count;
+  const int grid = total < sm_count * OCC ? total : sm_count * OCC;
   kern<<<grid, XPROP_THREADS, smem, s>>>(p, maps);
   return check_launch(BS == 32 ? "tcgen05_xprop_bs32" : "tcgen05_xprop_bs64");
 }
@@ -333,18 +385,26 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   p.sched = sched;
   p.n_ntiles = (N + 127) / 128;
   p.bprop = bprop;
+  p.y = y; p.y_pitch = (long long)Cout; p.N = N;
   // the schedule itself lives in device memory; its shape is passed by value
   p.n_ktiles = sched_tiles;
   p.groups_off = sched_groups_off;
   const int tile_blocks = sched_tile_blocks;
+  const int occ = (tile_blocks * bsize <= 256) ? 2 : 1;      // half-width tiles run two CTAs per SM
   if (p.n_ktiles <= 0 || tile_blocks <= 0 || tile_blocks > 512 / bsize || p.n_ktiles * tile_blocks < n_out ||
       sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
     return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
                 p.n_ktiles, tile_blocks, n_out);
-  if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true>(p, maps, dev.sm_count, s)
-                                             : launch_tc_xprop<32, false>(p, maps, dev.sm_count, s);
-  return dtype == BSMM_BF16 ? launch_tc_xprop<64, true>(p, maps, dev.sm_count, s)
-                            : launch_tc_xprop<64, false>(p, maps, dev.sm_count, s);
+  if (occ == 2) {
+    if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2>(p, maps, dev.sm_count, s)
+                                               : launch_tc_xprop<32, false, 2>(p, maps, dev.sm_count, s);
+    return dtype == BSMM_BF16 ? launch_tc_xprop<64, true, 2>(p, maps, dev.sm_count, s)
+                              : launch_tc_xprop<64, false, 2>(p, maps, dev.sm_count, s);
+  }
+  if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 1>(p, maps, dev.sm_count, s)
+                                             : launch_tc_xprop<32, false, 1>(p, maps, dev.sm_count, s);
+  return dtype == BSMM_BF16 ? launch_tc_xprop<64, true, 1>(p, maps, dev.sm_count, s)
+                            : launch_tc_xprop<64, false, 1>(p, maps, dev.sm_count, s);
 }
 
 inline int tc_bst_nt(int, int, int, const int32_t*, int, int, const void*, const void*, void*, int, int, int, int, int,

@@ -14,9 +14,14 @@ from . import _lib
 from .lut import MatmulLuts
 
 # tcgen05 tile width (output blocks whose accumulators share one CTA's tensor memory)
-_TILE_BLOCKS = {32: 16, 64: 8}
-# W blocks per schedule group == W slots per pipeline stage of the kernel (csrc/tc.cuh XpropCfg::WPS)
-_W_PER_GROUP = {32: 8, 64: 4}
+import os
+
+# Output blocks per xprop tile.  Full width (512 TMEM columns: 16 / 8 blocks) runs one CTA per SM; half width
+# (8 / 4 blocks) runs two CTAs -- two MMA-issuing threads -- per SM (csrc/tc.cuh XpropCfg<BS, OCC>).
+_HALF = os.environ.get("BSMM_XPROP_OCC", "2") == "2"
+_TILE_BLOCKS = {32: 8, 64: 4} if _HALF else {32: 16, 64: 8}
+# W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
+_W_PER_GROUP = ({32: 8, 64: 2} if _HALF else {32: 8, 64: 4})
 
 
 def _as_2d(t, axis, feat):
