@@ -117,7 +117,7 @@ def cpu_reference(density, axis, budget_s=20.0, steps=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--density", type=float, default=0.25)
@@ -151,6 +151,7 @@ def main():
     import torch
     import torch.distributed as dist
     from blocksparse_b200 import BlocksparseMatMul, _lib
+    from blocksparse_b200 import dist as bdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -173,8 +174,7 @@ def main():
         dx = bsmm.bprop(e, W)
         dw = bsmm.updat([x], [e])
         launches[0] += 3
-        if world > 1:
-            dist.all_reduce(dw)
+        bdist.allreduce_dw(dw)                 # no-op at world size 1
         return y, dx, dw
 
     def barrier():
@@ -201,7 +201,7 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
+    timed_samples = len(sampler.rows) if sampler else 0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -211,7 +211,7 @@ def main():
     value = flops_step_gpu * world / (ms_per_step * 1e-3) / 1e12
 
     # ---- per-kernel timing (each kernel alone, rotating inputs) for the roofline object
-    def time_op(fn, reps=20):
+    def time_op(fn, reps=50):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
@@ -228,6 +228,10 @@ def main():
     per_op["fprop"] = time_op(lambda i: bsmm.fprop(Xs[i % NSETS], W))
     per_op["bprop"] = time_op(lambda i: bsmm.bprop(Es[i % NSETS], W))
     per_op["updat"] = time_op(lambda i: bsmm.updat([Xs[i % NSETS]], [Es[i % NSETS]]))
+    clocks = None
+    if sampler:                      # sampled from the start of the timed region to the end of the per-kernel loops
+        clocks = sampler.stop()
+        clocks["samples_in_timed_region"] = timed_samples
     flops_op = 2.0 * bsmm.blocks * BS * BS * N
     bytes_op = 2.0 * (C * N + K * N) + 2.0 * bsmm.blocks * BS * BS
     dom = max(per_op, key=per_op.get)
@@ -238,7 +242,11 @@ def main():
         roof = {"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"]}
     else:
         roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
-    roof.update({"kernel": "%s (%s)" % (dom, kernels[dom]), "traffic": None, "peak_source": pk["source"],
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and abs(args.density - 0.25) < 1e-9:
+        traffic = json.load(open(tpath)).get(kernels[dom])
+    roof.update({"kernel": "%s (%s)" % (dom, kernels[dom]), "traffic": traffic, "peak_source": pk["source"],
                  "per_op_ms": per_op,
                  "per_op_tflops": {k: flops_op / (v * 1e-3) / 1e12 for k, v in per_op.items()},
                  "per_op_frac_tensor_peak": {k: flops_op / (v * 1e-3) / 1e12 / pk["tf_burst"] for k, v in per_op.items()},

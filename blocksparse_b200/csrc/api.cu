@@ -234,7 +234,7 @@ int bst_softmax(int x_dtype, int y_dtype, int bsize,
   BSMM_DISPATCH_DTYPE(x_dtype, TX, {
     BSMM_DISPATCH_DTYPE(y_dtype, TY, {
       BSMM_DISPATCH_BSIZE(bsize, BS, {
-        const long long groups = (long long)ctx_blks_q * (BS / (64 / BS));
+        const long long groups = (long long)ctx_blks_q * SoftmaxMap<BS>::GROUPS;
         dim3 grid((unsigned)((groups + SOFTMAX_WARPS - 1) / SOFTMAX_WARPS), heads, batch);
         bst_softmax_kernel<TX, TY, BS><<<grid, SOFTMAX_WARPS * 32, 0, s>>>(p);
       });
@@ -259,7 +259,7 @@ int bst_softmax_grad(int dtype, int dx_dtype, int bsize,
   BSMM_DISPATCH_DTYPE(dtype, T, {
     BSMM_DISPATCH_DTYPE(dx_dtype, TD, {
       BSMM_DISPATCH_BSIZE(bsize, BS, {
-        const long long groups = (long long)ctx_blks_q * (BS / (64 / BS));
+        const long long groups = (long long)ctx_blks_q * SoftmaxMap<BS>::GROUPS;
         dim3 grid((unsigned)((groups + SOFTMAX_WARPS - 1) / SOFTMAX_WARPS), heads, batch);
         bst_softmax_grad_kernel<T, TD, BS><<<grid, SOFTMAX_WARPS * 32, 0, s>>>(p);
       });

@@ -5,12 +5,12 @@
 //
 // HBM-bound: algorithmic traffic is (s_in + s_out) bytes per element of the
 // (batch, heads, blocks, bs, bs) tensor.  Work decomposition (differs from the
-// reference's one-CTA-per-query-row): one WARP owns 64/bs consecutive query rows of
-// one query block, so that every global access of the warp is a full, contiguous
-// 128-byte line of one bs x bs block (2 x 16-bit elements per lane); row statistics
-// are reduced with xor-shuffles inside the bs/2-lane group that shares a row.  The
-// row's values are held in registers between the statistics pass and the write pass
-// when the row has <= KEEP key blocks (the common case); longer rows re-read (L2 hits).
+// reference's one-CTA-per-query-row): one WARP owns 4 (bs 64) or 8 consecutive query
+// rows of one query block and each lane 16 bytes of a row, so every warp-wide access is
+// one contiguous 256..512-byte chunk of a block; the row's LUT entries are loaded once
+// (one per lane) and broadcast by shuffle; row statistics are reduced with xor-shuffles
+// inside the 4/8-lane group that shares a row.  Values stay in registers between the
+// statistics pass and the write pass for rows of <= KEEP key blocks; longer rows re-read.
 #pragma once
 #include <float.h>
 #include "common.cuh"
@@ -63,21 +63,67 @@ __device__ __forceinline__ uint64_t autoregress_word(uint64_t word, int ak, int 
 }
 
 constexpr int SOFTMAX_WARPS = 4;
-constexpr int SOFTMAX_KEEP = 16;    // key blocks of a row kept in registers
+
+// Lane mapping: a warp covers RP consecutive query rows of one block per pass; LPR lanes share a row and each
+// lane owns EPL consecutive keys (16 bytes of 16-bit data when bs >= 32), so one warp-wide load is a single
+// contiguous RP*bs*sizeof(T) chunk of the block (512 B for bs 64).
+template <int BS> struct SoftmaxMap {
+  static constexpr int LPR = (BS == 64) ? 8 : 4;        // lanes per row
+  static constexpr int EPL = BS / LPR;                  // elements per lane: 8, 8, 4, 2
+  static constexpr int RP = 32 / LPR;                   // rows per pass: 4, 8, 8, 8
+  static constexpr int GROUPS = BS / RP;                // passes per query block
+  static constexpr int KEEP = (EPL >= 8) ? 8 : 16;      // key blocks of a row kept in registers
+};
+
+template <typename T, int EPL> __device__ __forceinline__ void load_vec(const T* p, float (&f)[EPL]) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) { const float2 v = *reinterpret_cast<const float2*>(p + i); f[i] = v.x; f[i + 1] = v.y; }
+  } else if constexpr (EPL == 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const typename Pair<T>::type h = *reinterpret_cast<const typename Pair<T>::type*>(&w[i]); f[2 * i] = to_f32<T>(h.x); f[2 * i + 1] = to_f32<T>(h.y); }
+  } else if constexpr (EPL == 4) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const typename Pair<T>::type h = *reinterpret_cast<const typename Pair<T>::type*>(&w[i]); f[2 * i] = to_f32<T>(h.x); f[2 * i + 1] = to_f32<T>(h.y); }
+  } else {
+    const float2 v = load2<T>(p); f[0] = v.x; f[1] = v.y;
+  }
+}
+template <typename T, int EPL> __device__ __forceinline__ void store_vec(T* p, const float (&f)[EPL]) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(f[i], f[i + 1]);
+  } else if constexpr (EPL == 8) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { typename Pair<T>::type h; h.x = from_f32<T>(f[2 * i]); h.y = from_f32<T>(f[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if constexpr (EPL == 4) {
+    uint32_t w[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { typename Pair<T>::type h; h.x = from_f32<T>(f[2 * i]); h.y = from_f32<T>(f[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+  } else {
+    store2<T>(p, f[0], f[1]);
+  }
+}
 
 template <typename TX, typename TY, int BS>
 __global__ void __launch_bounds__(SOFTMAX_WARPS * 32)
 bst_softmax_kernel(const SoftmaxParams p) {
   using MT = typename MaskWord<BS>::type;
-  constexpr int R = 64 / BS;               // rows per warp
-  constexpr int GROUPS = BS / R;           // row groups per query block
-  constexpr int HALF = BS / 2;             // lanes per row
+  using M = SoftmaxMap<BS>;
+  constexpr int LPR = M::LPR, EPL = M::EPL, RP = M::RP, GROUPS = M::GROUPS, KEEP = M::KEEP;
   const int lane = threadIdx.x % 32;
   const long long gid = (long long)blockIdx.x * SOFTMAX_WARPS + threadIdx.x / 32;
   if (gid >= (long long)p.ctx_blks_q * GROUPS) return;
   const int q = (int)(gid / GROUPS);
-  const int row = (int)(gid % GROUPS) * R + lane / HALF;
-  const int col = (lane % HALF) * 2;
+  const int row = (int)(gid % GROUPS) * RP + lane / LPR;
+  const int col = (lane % LPR) * EPL;
   const int h = blockIdx.y, b = blockIdx.z;
 
   const int hl = p.nn_head_stride ? h : 0;
@@ -85,128 +131,152 @@ bst_softmax_kernel(const SoftmaxParams p) {
   const int first = lut[2 * q], count = lut[2 * q + 1];
   if (count == 0) return;
   const long long zoff = ((long long)b * p.heads + h) * p.blocks;
-  const TX* x = reinterpret_cast<const TX*>(p.x);
-  TY* y = reinterpret_cast<TY*>(p.y);
+  const TX* x = reinterpret_cast<const TX*>(p.x) + (long long)row * BS + col;
+  TY* y = reinterpret_cast<TY*>(p.y) + (long long)row * BS + col;
   const MT* mask = reinterpret_cast<const MT*>(p.mask);
-  if (mask) mask += (p.mask_head_stride ? (long long)h * p.mask_head_stride : 0);
-  const int32_t* nt = p.nt_lut ? p.nt_lut + (long long)hl * p.nt_head_stride : nullptr;
-  (void)nt;
+  if (mask) mask += (p.mask_head_stride ? (long long)h * p.mask_head_stride : 0) + row;
+  // the row's LUT entries, one per lane (rows longer than 32 key blocks reload per chunk of 32)
+  const int2* ent = reinterpret_cast<const int2*>(lut) + first;
+  int2 my = (lane < count) ? ent[lane] : make_int2(0, 0);
 
-  auto load_entry = [&](int e, float& v0, float& v1) {
-    const int blk = lut[2 * (first + e)];
-    const int kb = lut[2 * (first + e) + 1];
-    float2 v = load2<TX>(x + (zoff + blk) * (BS * BS) + row * BS + col);
-    v0 = v.x * p.scale; v1 = v.y * p.scale;
+  auto entry = [&](int e, int& blk, int& kb) {
+    if (e < 32) { blk = __shfl_sync(0xffffffffu, my.x, e); kb = __shfl_sync(0xffffffffu, my.y, e); }
+    else { const int2 v = ent[e]; blk = v.x; kb = v.y; }
+  };
+  auto load_entry = [&](int e, float (&v)[EPL]) {
+    int blk, kb;
+    entry(e, blk, kb);
+    load_vec<TX, EPL>(x + (zoff + blk) * (BS * BS), v);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] *= p.scale;
     if (mask) {
-      uint64_t w = (uint64_t)mask[(long long)blk * BS + row];
+      uint64_t w = (uint64_t)mask[(long long)blk * BS];
       if (p.autoregress_at_key >= 0) w = autoregress_word<BS>(w, p.autoregress_at_key, kb, q * BS + row);
-      if (!((w >> col) & 1ull)) v0 = -FLT_MAX;
-      if (!((w >> (col + 1)) & 1ull)) v1 = -FLT_MAX;
+      w >>= col;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) if (!((w >> i) & 1ull)) v[i] = -FLT_MAX;
     }
   };
 
-  float keep0[SOFTMAX_KEEP], keep1[SOFTMAX_KEEP];
+  float keep[KEEP][EPL];
   float m = -FLT_MAX;
 #pragma unroll
-  for (int e = 0; e < SOFTMAX_KEEP; ++e) {
-    keep0[e] = keep1[e] = -FLT_MAX;
+  for (int e = 0; e < KEEP; ++e) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) keep[e][i] = -FLT_MAX;
     if (e < count) {
-      load_entry(e, keep0[e], keep1[e]);
-      m = fmaxf(m, fmaxf(keep0[e], keep1[e]));
+      load_entry(e, keep[e]);
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) m = fmaxf(m, keep[e][i]);
     }
   }
-  for (int e = SOFTMAX_KEEP; e < count; ++e) {
-    float v0, v1; load_entry(e, v0, v1);
-    m = fmaxf(m, fmaxf(v0, v1));
+  for (int e = KEEP; e < count; ++e) {
+    float v[EPL]; load_entry(e, v);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) m = fmaxf(m, v[i]);
   }
 #pragma unroll
-  for (int o = HALF / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  for (int o = LPR / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
 
   constexpr float LOG2E = 1.4426950408889634f;
   float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < SOFTMAX_KEEP; ++e) {
+  for (int e = 0; e < KEEP; ++e) {
     if (e < count) {
-      keep0[e] = exp2f((keep0[e] - m) * LOG2E);
-      keep1[e] = exp2f((keep1[e] - m) * LOG2E);
-      s += keep0[e] + keep1[e];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) { keep[e][i] = exp2f((keep[e][i] - m) * LOG2E); s += keep[e][i]; }
     }
   }
-  for (int e = SOFTMAX_KEEP; e < count; ++e) {
-    float v0, v1; load_entry(e, v0, v1);
-    s += exp2f((v0 - m) * LOG2E) + exp2f((v1 - m) * LOG2E);
+  for (int e = KEEP; e < count; ++e) {
+    float v[EPL]; load_entry(e, v);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) s += exp2f((v[i] - m) * LOG2E);
   }
 #pragma unroll
-  for (int o = HALF / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float inv = 1.f / s;
 
 #pragma unroll
-  for (int e = 0; e < SOFTMAX_KEEP; ++e) {
+  for (int e = 0; e < KEEP; ++e) {
     if (e < count) {
-      const int blk = lut[2 * (first + e)];
-      store2<TY>(y + (zoff + blk) * (BS * BS) + row * BS + col, keep0[e] * inv, keep1[e] * inv);
+      int blk, kb; entry(e, blk, kb);
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) keep[e][i] *= inv;
+      store_vec<TY, EPL>(y + (zoff + blk) * (BS * BS), keep[e]);
     }
   }
-  for (int e = SOFTMAX_KEEP; e < count; ++e) {
-    float v0, v1; load_entry(e, v0, v1);
-    const int blk = lut[2 * (first + e)];
-    store2<TY>(y + (zoff + blk) * (BS * BS) + row * BS + col,
-               exp2f((v0 - m) * LOG2E) * inv, exp2f((v1 - m) * LOG2E) * inv);
+  for (int e = KEEP; e < count; ++e) {
+    float v[EPL]; load_entry(e, v);
+    int blk, kb; entry(e, blk, kb);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] = exp2f((v[i] - m) * LOG2E) * inv;
+    store_vec<TY, EPL>(y + (zoff + blk) * (BS * BS), v);
   }
 }
 
 template <typename T, typename TD, int BS>
 __global__ void __launch_bounds__(SOFTMAX_WARPS * 32)
 bst_softmax_grad_kernel(const SoftmaxParams p) {
-  constexpr int R = 64 / BS;
-  constexpr int GROUPS = BS / R;
-  constexpr int HALF = BS / 2;
+  using M = SoftmaxMap<BS>;
+  constexpr int LPR = M::LPR, EPL = M::EPL, RP = M::RP, GROUPS = M::GROUPS, KEEP = M::KEEP / 2 < 4 ? 4 : M::KEEP / 2;
   const int lane = threadIdx.x % 32;
   const long long gid = (long long)blockIdx.x * SOFTMAX_WARPS + threadIdx.x / 32;
   if (gid >= (long long)p.ctx_blks_q * GROUPS) return;
   const int q = (int)(gid / GROUPS);
-  const int row = (int)(gid % GROUPS) * R + lane / HALF;
-  const int col = (lane % HALF) * 2;
+  const int row = (int)(gid % GROUPS) * RP + lane / LPR;
+  const int col = (lane % LPR) * EPL;
   const int h = blockIdx.y, b = blockIdx.z;
   const int hl = p.nn_head_stride ? h : 0;
   const int32_t* lut = p.nn_lut + (long long)hl * p.nn_head_stride;
   const int first = lut[2 * q], count = lut[2 * q + 1];
   if (count == 0) return;
   const long long zoff = ((long long)b * p.heads + h) * p.blocks;
-  const T* dy = reinterpret_cast<const T*>(p.x);
-  const T* yv = reinterpret_cast<const T*>(p.y_in);
-  TD* dx = reinterpret_cast<TD*>(p.y);
+  const long long roff = (long long)row * BS + col;
+  const T* dy = reinterpret_cast<const T*>(p.x) + roff;
+  const T* yv = reinterpret_cast<const T*>(p.y_in) + roff;
+  TD* dx = reinterpret_cast<TD*>(p.y) + roff;
+  const int2* ent = reinterpret_cast<const int2*>(lut) + first;
+  const int my = (lane < count) ? ent[lane].x : 0;
+  auto block_of = [&](int e) { return e < 32 ? __shfl_sync(0xffffffffu, my, e) : ent[e].x; };
 
-  float kd0[SOFTMAX_KEEP], kd1[SOFTMAX_KEEP], ky0[SOFTMAX_KEEP], ky1[SOFTMAX_KEEP];
+  float kd[KEEP][EPL], ky[KEEP][EPL];
   float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < SOFTMAX_KEEP; ++e) {
-    kd0[e] = kd1[e] = ky0[e] = ky1[e] = 0.f;
+  for (int e = 0; e < KEEP; ++e) {
     if (e < count) {
-      const long long off = (zoff + lut[2 * (first + e)]) * (BS * BS) + row * BS + col;
-      float2 d = load2<T>(dy + off), v = load2<T>(yv + off);
-      kd0[e] = d.x; kd1[e] = d.y; ky0[e] = v.x; ky1[e] = v.y;
-      s += d.x * v.x + d.y * v.y;
+      const long long off = (zoff + block_of(e)) * (BS * BS);
+      load_vec<T, EPL>(dy + off, kd[e]);
+      load_vec<T, EPL>(yv + off, ky[e]);
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) s += kd[e][i] * ky[e][i];
     }
   }
-  for (int e = SOFTMAX_KEEP; e < count; ++e) {
-    const long long off = (zoff + lut[2 * (first + e)]) * (BS * BS) + row * BS + col;
-    float2 d = load2<T>(dy + off), v = load2<T>(yv + off);
-    s += d.x * v.x + d.y * v.y;
+  for (int e = KEEP; e < count; ++e) {
+    const long long off = (zoff + block_of(e)) * (BS * BS);
+    float d[EPL], v[EPL];
+    load_vec<T, EPL>(dy + off, d); load_vec<T, EPL>(yv + off, v);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) s += d[i] * v[i];
   }
 #pragma unroll
-  for (int o = HALF / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
 #pragma unroll
-  for (int e = 0; e < SOFTMAX_KEEP; ++e) {
+  for (int e = 0; e < KEEP; ++e) {
     if (e < count) {
-      const long long off = (zoff + lut[2 * (first + e)]) * (BS * BS) + row * BS + col;
-      store2<TD>(dx + off, (kd0[e] - s) * ky0[e] * p.scale, (kd1[e] - s) * ky1[e] * p.scale);
+      const long long off = (zoff + block_of(e)) * (BS * BS);
+      float o[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) o[i] = (kd[e][i] - s) * ky[e][i] * p.scale;
+      store_vec<TD, EPL>(dx + off, o);
     }
   }
-  for (int e = SOFTMAX_KEEP; e < count; ++e) {
-    const long long off = (zoff + lut[2 * (first + e)]) * (BS * BS) + row * BS + col;
-    float2 d = load2<T>(dy + off), v = load2<T>(yv + off);
-    store2<TD>(dx + off, (d.x - s) * v.x * p.scale, (d.y - s) * v.y * p.scale);
+  for (int e = KEEP; e < count; ++e) {
+    const long long off = (zoff + block_of(e)) * (BS * BS);
+    float d[EPL], v[EPL];
+    load_vec<T, EPL>(dy + off, d); load_vec<T, EPL>(yv + off, v);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) d[i] = (d[i] - s) * v[i] * p.scale;
+    store_vec<TD, EPL>(dx + off, d);
   }
 }
 

@@ -5,7 +5,7 @@ timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.txt 2>&1; e
 tail -12 gpurun_out/pytest_gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.txt
 tail -2 gpurun_out/smoke.txt
-timeout 900 python bench.py --sweep > gpurun_out/bench.txt 2>&1; echo "bench rc=$?" >> gpurun_out/bench.txt
+timeout 900 python bench.py --sweep --steps 300 > gpurun_out/bench.txt 2>&1; echo "bench rc=$?" >> gpurun_out/bench.txt
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.txt 2>&1
 timeout 300 python tools/bench_bst.py > gpurun_out/bench_bst.txt 2>&1; echo "bst rc=$?" >> gpurun_out/bench_bst.txt
 cat gpurun_out/bench_bst.txt | cut -c1-200
