@@ -98,6 +98,7 @@ struct XpropTcParams {
   int n_ktiles;              // output tiles along the feature axis
   int n_ntiles;              // ceil(N / 128)
   int bprop;
+  int axis0;                 // activations are (C, N): A operand is MN-major, output is stored transposed
   void* y;                   // output base, row pitch and row count (direct-store epilogue)
   long long y_pitch;         // elements
   int N;
@@ -148,7 +149,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     // gc % XPROP_PRODUCERS == warp; lane i holds int i of the group record.
     uint32_t gbase = 0;                   // groups of earlier tiles
     bool alive = true;
-    const uint32_t p_idesc0 = ptx::make_idesc_f16(BF16, false, !p.bprop, 128, 0);
+    const uint32_t p_idesc0 = ptx::make_idesc_f16(BF16, p.axis0 != 0, !p.bprop, 128, 0);
     const uint32_t p_bdesc_lo = (uint32_t)ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
       const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
@@ -181,7 +182,12 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         uint8_t* stage = sStage + st * STAGE_BYTES;
         if (lane == 0) {
           ptx::mbar_expect_tx(&full[st], XBYTES + (uint32_t)n_w * WBYTES);
-          ptx::tma_load_2d(stage, &maps.x, &full[st], in_blk * BS, nt * 128);
+          if (!p.axis0) {
+            ptx::tma_load_2d(stage, &maps.x, &full[st], in_blk * BS, nt * 128);          // [128 n][bs c], K-major A
+          } else {                                                                      // [bs c][128 n] as two 64-wide boxes, MN-major A
+            ptx::tma_load_2d(stage, &maps.x, &full[st], nt * 128, in_blk * BS);
+            ptx::tma_load_2d(stage + XBYTES / 2, &maps.x, &full[st], nt * 128 + 64, in_blk * BS);
+          }
         }
         if (lane >= 4 && lane < 4 + n_w)
           ptx::tma_load_2d(stage + XBYTES + (lane - 4) * WBYTES, &maps.w, &full[st], 0, cur * BS);
@@ -194,7 +200,11 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     // fprop: B = W[c][k] read as K x N with N contiguous (MN-major): K=16 slice = 16 rows, blocks LBO apart.
     // bprop: B = W[c][k] read as N x K with K contiguous (K-major):  K=16 slice = 32 bytes along the row.
     const uint32_t b_kstep16 = (p.bprop ? 32u : 16u * ROW) >> 4;
-    const uint64_t a_desc0 = ptx::make_smem_desc(ptx::smem_u32(sStage), 16, Cfg::SBO, Cfg::SWZ);
+    // axis 1: A = X[n][c] tile, K-major, rows of bs*2 bytes, K=16 slice = +32 B.
+    // axis 0: A = X[c][n] tile, MN-major SW128: two [bs x 64] boxes (LBO = box), 8-row groups 1 KB apart, K=16 slice = 16 rows.
+    const uint64_t a_desc0 = p.axis0 ? ptx::make_smem_desc(ptx::smem_u32(sStage), XBYTES / 2, 1024, ptx::SWZ_128B)
+                                     : ptx::make_smem_desc(ptx::smem_u32(sStage), 16, Cfg::SBO, Cfg::SWZ);
+    const uint32_t a_kstep16 = p.axis0 ? (16u * 128u) >> 4 : 2u;
     const uint32_t b_desc_hi = (uint32_t)(ptx::make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) >> 32);
     uint32_t gc = 0, tile_it = 0;
     bool alive = true;
@@ -217,7 +227,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
           for (int r = 0; r < 8; ++r) c[r] = cmd[st][r];
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t adesc = a_st + (uint64_t)(ks * 2);
+            const uint64_t adesc = a_st + (uint64_t)(ks * a_kstep16);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
               if (r >= n_runs) break;              // a real (uniform) branch: skipped runs cost nothing
@@ -250,7 +260,37 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*abort_flag) { g_tc_error = 6; break; }       // uniform across the 128 epilogue threads
       ptx::tc_fence_after();
-      if constexpr (STG == 0) {
+      if (p.axis0) {
+        // Y is (K, N): lane = minibatch column, register j = output feature -> for every j a warp writes 32
+        // consecutive 16-bit values (one 64-byte segment); no staging needed.
+        const long long gcol = (long long)nt * 128 + row;
+        uint16_t* ycol = reinterpret_cast<uint16_t*>(p.y) + (long long)first_out * BS * p.y_pitch + gcol;
+        for (int slot = 0; slot < n_out; ++slot) {
+#pragma unroll
+          for (int h = 0; h < BS / 32; ++h) {
+            uint32_t v[32];
+            if ((mask >> slot) & 1u) {
+              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
+              ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            if (gcol < p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                uint16_t o;
+                if (BF16) { __nv_bfloat16 q = __float2bfloat16_rn(__uint_as_float(v[j])); o = *reinterpret_cast<uint16_t*>(&q); }
+                else      { __half q = __float2half_rn(__uint_as_float(v[j]));            o = *reinterpret_cast<uint16_t*>(&q); }
+                ycol[(long long)(slot * BS + h * 32 + j) * p.y_pitch] = o;
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) ptx::mbar_arrive(&acc_empty);
+      } else if constexpr (STG == 0) {
         // direct epilogue: thread = one row of the tile; BS 16-bit outputs = one contiguous row segment per block
         const long long grow = (long long)nt * 128 + row;
         uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + grow * p.y_pitch + (long long)first_out * BS;
@@ -362,9 +402,9 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
                     int sched_groups_off, cudaStream_t s) {
   (void)lut;
   if (dtype != BSMM_F16 && dtype != BSMM_BF16) { fail(0, "fp32 runs on the FMA path"); return TC_NOT_APPLICABLE; }
-  if (axis != 1) { fail(0, "feature_axis 0 has no tcgen05 xprop kernel yet"); return TC_NOT_APPLICABLE; }
   if (bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
   if (gate != nullptr) { fail(0, "gated xprop uses the CUDA-core path"); return TC_NOT_APPLICABLE; }
+  if (axis == 0 && (N & 7)) { fail(0, "feature_axis 0 needs N %% 8 == 0 for TMA (row pitch multiple of 16 bytes)"); return TC_NOT_APPLICABLE; }
   if (sched == nullptr || sched_tiles <= 0) { fail(0, "no tile schedule supplied"); return TC_NOT_APPLICABLE; }
   if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) { fail(0, "pointers must be 16-byte aligned for TMA"); return TC_NOT_APPLICABLE; }
   const DeviceInfo& dev = device_info();
@@ -377,7 +417,11 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   const uint64_t Cin = (uint64_t)n_in * bsize, Cout = (uint64_t)n_out * bsize;
   XpropTmaps maps;
   const CUtensorMapSwizzle swz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  if (int e = make_tmap_2d(&maps.x, dtype, x, Cin, (uint64_t)N, Cin, bsize, 128, swz)) return e;
+  if (axis == 1) {
+    if (int e = make_tmap_2d(&maps.x, dtype, x, Cin, (uint64_t)N, Cin, bsize, 128, swz)) return e;
+  } else {       // (C, N): inner dim = minibatch; box = 64 columns x bs feature rows, 128-byte rows
+    if (int e = make_tmap_2d(&maps.x, dtype, x, (uint64_t)N, Cin, (uint64_t)N, 64, bsize, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  }
   if (int e = make_tmap_2d(&maps.w, dtype, w, (uint64_t)bsize, (uint64_t)blocks * bsize, (uint64_t)bsize, bsize, bsize, swz)) return e;
   if (int e = make_tmap_2d(&maps.y, dtype, y, Cout, (uint64_t)N, Cout, bsize, 128, swz)) return e;
 
@@ -385,7 +429,8 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   p.sched = sched;
   p.n_ntiles = (N + 127) / 128;
   p.bprop = bprop;
-  p.y = y; p.y_pitch = (long long)Cout; p.N = N;
+  p.axis0 = axis == 0;
+  p.y = y; p.y_pitch = axis == 0 ? (long long)N : (long long)Cout; p.N = N;
   // the schedule itself lives in device memory; its shape is passed by value
   p.n_ktiles = sched_tiles;
   p.groups_off = sched_groups_off;

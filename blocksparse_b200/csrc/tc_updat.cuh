@@ -33,6 +33,7 @@ struct UpdatTcParams {
   int k_per_tile;           // KT: slots per tile (record stride for the block table)
   int N;                    // minibatch rows per pair
   int pcount;
+  int axis0;                // activations are (C, N): both operands K-major
   float alpha, beta;
   const float* gate;        // optional, only with gated
   int gated;
@@ -94,24 +95,37 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
         uint8_t* stage = smem + st * STAGE_BYTES;
         if (lane == 0) ptx::mbar_expect_tx(&full[st], ABYTES + (uint32_t)n_act * BSLOT);
         __syncwarp();
-        if (lane < 2)
-          ptx::tma_load_2d(stage + lane * (ABYTES / 2), &maps.x[pair], &full[st], c0 * BS + lane * 64, n0);
-        else if (lane < 2 + n_act)
-          ptx::tma_load_2d(stage + ABYTES + (lane - 2) * BSLOT, &maps.dy[pair], &full[st], my_k * BS, n0);
+        if (!p.axis0) {
+          if (lane < 2)
+            ptx::tma_load_2d(stage + lane * (ABYTES / 2), &maps.x[pair], &full[st], c0 * BS + lane * 64, n0);
+          else if (lane < 2 + n_act)
+            ptx::tma_load_2d(stage + ABYTES + (lane - 2) * BSLOT, &maps.dy[pair], &full[st], my_k * BS, n0);
+        } else {
+          if (lane == 0)           // [128 features][64 n], 128-byte rows
+            ptx::tma_load_2d(stage, &maps.x[pair], &full[st], n0, c0 * BS);
+          else if (lane >= 2 && lane < 2 + n_act)
+            ptx::tma_load_2d(stage + ABYTES + (lane - 2) * BSLOT, &maps.dy[pair], &full[st], n0, my_k * BS);
+        }
         __syncwarp();
       }
       sbase += n_chunks;
     }
   } else if (warp == 2) {
     // ================================ MMA issuer ================================
-    const uint64_t a_desc0 = ptx::make_smem_desc(ptx::smem_u32(smem), ABYTES / 2, 1024, ptx::SWZ_128B);
-    const uint64_t b_desc0 = ptx::make_smem_desc(ptx::smem_u32(smem) + ABYTES, BSLOT, B_SBO, B_SWZ);
+    // axis 1: A = X[n][c] (MN-major, two 64-feature boxes), B = DY[n][k] (MN-major, one box per kept block).
+    // axis 0: A = X[c][n], B = DY[k][n]: both K-major with 128-byte rows; kept blocks continue the row index.
+    const uint64_t a_desc0 = p.axis0 ? ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, ptx::SWZ_128B)
+                                     : ptx::make_smem_desc(ptx::smem_u32(smem), ABYTES / 2, 1024, ptx::SWZ_128B);
+    const uint64_t b_desc0 = p.axis0 ? ptx::make_smem_desc(ptx::smem_u32(smem) + ABYTES, 16, 1024, ptx::SWZ_128B)
+                                     : ptx::make_smem_desc(ptx::smem_u32(smem) + ABYTES, BSLOT, B_SBO, B_SWZ);
+    const uint32_t a_kstep16 = p.axis0 ? 2u : (2048u >> 4);
+    const uint32_t b_kstep16 = p.axis0 ? 2u : (B_KSTEP >> 4);
     uint32_t sc = 0, tile_it = 0;
     bool alive = true;
     for (int t = blockIdx.x; t < p.n_tiles && alive; t += gridDim.x, ++tile_it) {
       const int n_act = recs[(size_t)t * 64 + 1];
       const uint32_t buf = tile_it & 1;
-      const uint32_t idesc = ptx::make_idesc_f16(BF16, true, true, 128, n_act * BS);
+      const uint32_t idesc = ptx::make_idesc_f16(BF16, !p.axis0, !p.axis0, 128, n_act * BS);
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty[buf], ((tile_it >> 1) & 1) ^ 1, abort_flag))) { g_tc_error = 13; break; }
       ptx::tc_fence_after();
       const uint32_t d = tmem + buf * 256;
@@ -124,7 +138,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
           const uint64_t b_st = b_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
 #pragma unroll
           for (int ks = 0; ks < UPDAT_KCHUNK / 16; ++ks)
-            ptx::mma_ss(d, a_st + (uint64_t)((ks * 2048) >> 4), b_st + (uint64_t)((ks * B_KSTEP) >> 4), idesc,
+            ptx::mma_ss(d, a_st + (uint64_t)(ks * a_kstep16), b_st + (uint64_t)(ks * b_kstep16), idesc,
                         (ch > 0 || ks > 0) ? 1u : 0u);
           ptx::tc_commit(&empty[st]);
         }
@@ -236,7 +250,7 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
                     int sched_groups_off, cudaStream_t s) {
   (void)updat_lut; (void)blocks; (void)sched_groups_off;
   if (dtype != BSMM_F16 && dtype != BSMM_BF16) { fail(0, "fp32 runs on the FMA path"); return TC_NOT_APPLICABLE; }
-  if (axis != 1) { fail(0, "feature_axis 0 has no tcgen05 updat kernel yet"); return TC_NOT_APPLICABLE; }
+  if (axis == 0 && (N & 7)) { fail(0, "feature_axis 0 needs N %% 8 == 0 for TMA"); return TC_NOT_APPLICABLE; }
   if (bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
   if (sched == nullptr || sched_tiles <= 0) { fail(0, "no updat schedule supplied"); return TC_NOT_APPLICABLE; }
   if (sched_tile_blocks != 256 / bsize) return fail(BSMM_E_ARG, "bsmm_updat: schedule built for %d slots per tile, kernel needs %d", sched_tile_blocks, 256 / bsize);
@@ -254,10 +268,16 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   memset(&maps, 0, sizeof(maps));
   const CUtensorMapSwizzle bswz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int i = 0; i < pcount; ++i) {
-    if (int e = make_tmap_2d(&maps.x[i], dtype, xs[i], C, (uint64_t)N, C, 64, UPDAT_KCHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-    if (int e = make_tmap_2d(&maps.dy[i], dtype, dys[i], K, (uint64_t)N, K, bsize, UPDAT_KCHUNK, bswz)) return e;
+    if (axis == 1) {
+      if (int e = make_tmap_2d(&maps.x[i], dtype, xs[i], C, (uint64_t)N, C, 64, UPDAT_KCHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+      if (int e = make_tmap_2d(&maps.dy[i], dtype, dys[i], K, (uint64_t)N, K, bsize, UPDAT_KCHUNK, bswz)) return e;
+    } else {       // (features, N): inner dim = minibatch, 64 columns = 128-byte rows
+      if (int e = make_tmap_2d(&maps.x[i], dtype, xs[i], (uint64_t)N, C, (uint64_t)N, UPDAT_KCHUNK, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+      if (int e = make_tmap_2d(&maps.dy[i], dtype, dys[i], (uint64_t)N, K, (uint64_t)N, UPDAT_KCHUNK, bsize, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
   }
   UpdatTcParams p;
+  p.axis0 = axis == 0;
   p.sched = sched; p.n_tiles = sched_tiles; p.k_per_tile = sched_tile_blocks; p.N = N; p.pcount = pcount;
   p.alpha = alpha; p.beta = beta; p.gate = gate; p.gated = (gated_dw && gate) ? 1 : 0; p.dw = dw;
   const bool bf = dtype == BSMM_BF16;

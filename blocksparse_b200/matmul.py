@@ -118,7 +118,7 @@ class BlocksparseMatMul(object):
                 "bprop": torch.as_tensor(self._luts.bprop_rows, device=device),
                 "updat": torch.as_tensor(self.updat_lut, device=device),
             }
-            tb = _TILE_BLOCKS.get(self.bsize) if self.axis == 1 else None
+            tb = _TILE_BLOCKS.get(self.bsize)
             if tb:
                 wpg = _W_PER_GROUP[self.bsize]
                 fs, foff = self._luts.tile_schedule(False, tb, self.bsize, wpg)

@@ -36,14 +36,18 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("axis", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("case", CASES)
-def test_tc_xprop_matches_oracle(case, dtype):
+def test_tc_xprop_matches_oracle(case, dtype, axis):
     CB, KB, density, N, bs = case
+    if axis == 0:
+        N = max(8, (N + 7) // 8 * 8)          # TMA needs a 16-byte row pitch when the minibatch is the inner dim
     rng = np.random.default_rng(CB * 1000 + KB * 10 + N)
     lay = layout(rng, CB, KB, density, empty_col=KB // 2 if density < 1 else None, empty_row=1 if density < 1 and CB > 2 else None)
-    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=1)
-    orc = MatmulOracle(lay, bs, 1)
+    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=axis)
+    orc = MatmulOracle(lay, 32, axis)         # (axis 0, bs 64) is outside the reference's pairs: reuse the dense restatement
+    orc.bsize, orc.C, orc.K, orc.w_shape = bs, CB * bs, KB * bs, bsmm.w_shape
     W = torch.as_tensor(rng.normal(0, 0.1, bsmm.w_shape).astype(np.float32)).to(dtype)
     X = torch.as_tensor(rng.normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).to(dtype)
     E = torch.as_tensor(rng.normal(0, 1, bsmm.o_shape(N)).astype(np.float32)).to(dtype)
@@ -89,14 +93,18 @@ UPDAT_CASES = [
 ]
 
 
+@pytest.mark.parametrize("axis", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("case", UPDAT_CASES)
-def test_tc_updat_matches_oracle(case, dtype):
+def test_tc_updat_matches_oracle(case, dtype, axis):
     CB, KB, density, N, bs, pairs = case
+    if axis == 0:
+        N = max(8, (N + 7) // 8 * 8)
     rng = np.random.default_rng(CB * 1000 + KB * 10 + N + 7)
     lay = layout(rng, CB, KB, density, empty_col=KB // 2 if density < 1 else None, empty_row=1 if density < 1 and CB > 2 else None)
-    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=1)
-    orc = MatmulOracle(lay, bs, 1)
+    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=axis)
+    orc = MatmulOracle(lay, 32, axis)
+    orc.bsize, orc.C, orc.K, orc.w_shape = bs, CB * bs, KB * bs, bsmm.w_shape
     xs, es, ref = [], [], np.zeros(bsmm.w_shape)
     for _ in range(pairs):
         X = torch.as_tensor(rng.normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).to(dtype)
