@@ -142,6 +142,7 @@ static int check_bst(int bsize, int lut_heads, int heads, int head_state, int ba
 
 int bst_nt(int dtype, int c_dtype, int bsize,
            const int32_t* nt_lut, int lut_heads, int blocks,
+           const int32_t* nt_items, int n_items,
            const void* a, const void* b, void* c,
            int batch, int heads, int head_state, int ctx_blks_a, int ctx_blks_b,
            int flags, void* stream) {
@@ -153,7 +154,7 @@ int bst_nt(int dtype, int c_dtype, int bsize,
   cudaStream_t s = (cudaStream_t)stream;
 
   if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
-    int rc = tc_bst_nt(dtype, c_dtype, bsize, nt_lut, lut_heads, blocks, a, b, c, batch, heads, head_state,
+    int rc = tc_bst_nt(dtype, c_dtype, bsize, nt_items, n_items, lut_heads, blocks, a, b, c, batch, heads, head_state,
                        ctx_blks_a, ctx_blks_b, s);
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC) return fail(BSMM_E_ARG, "bst_nt: no tcgen05 kernel for this configuration (%s)", err_buf());

@@ -452,10 +452,8 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
                             : launch_tc_xprop<64, false, 1>(p, maps, dev.sm_count, s);
 }
 
-inline int tc_bst_nt(int, int, int, const int32_t*, int, int, const void*, const void*, void*, int, int, int, int, int,
-                     cudaStream_t) { return TC_NOT_APPLICABLE; }
-inline int tc_bst_xn(int, int, int, int, const int32_t*, int, int, int, const void*, const void*, void*, int, int, int,
-                     int, int, cudaStream_t) { return TC_NOT_APPLICABLE; }
 }  // namespace bsmm
 
 #include "tc_updat.cuh"
+#include "softmax.cuh"
+#include "tc_bst.cuh"

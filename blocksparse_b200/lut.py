@@ -356,6 +356,33 @@ def xn_lut(outs, ins, n_out):
     return lut, rows, longest
 
 
+def build_nt_items(tn_rows_per_head):
+    """Schedule for the tcgen05 NT kernel (csrc/tc_bst.cuh): blocks that share a key block, two at a time.
+
+    tn_rows_per_head[h][k] = [(block_id, q_block), ...] (the reference's tn_list).  Returns int32
+    [lut_heads][n_items][8] = (k_blk, n_valid, blk0, q0, blk1, q1, 0, 0); heads with fewer pairs are padded with
+    n_valid = 0 items.
+    """
+    per_head = []
+    for rows in tn_rows_per_head:
+        items = []
+        for k, row in enumerate(rows):
+            for i in range(0, len(row), 2):
+                b0, q0 = row[i]
+                if i + 1 < len(row):
+                    b1, q1 = row[i + 1]
+                    items.append((k, 2, b0, q0, b1, q1, 0, 0))
+                else:
+                    items.append((k, 1, b0, q0, 0, 0, 0, 0))
+        per_head.append(items)
+    n = max(len(it) for it in per_head)
+    out = np.zeros((len(per_head), n, 8), dtype=np.int32)
+    for h, items in enumerate(per_head):
+        if items:
+            out[h, :len(items)] = np.array(items, dtype=np.int32)
+    return out
+
+
 class TransformerLuts(object):
     """Everything BlocksparseTransformer derives from a (heads|1, q_blks, k_blks) layout."""
 
@@ -391,6 +418,7 @@ class TransformerLuts(object):
         self.nt_lut = np.stack(nt_luts)
         self.nn_lut = np.stack(nn_luts)
         self.tn_lut = np.stack(tn_luts)
+        self.nt_items = build_nt_items(self.tn_list)
         self.softmax_mask = self.softmax_mask_np = None
         if mask_callback is not None:
             self.init_softmax_mask(mask_callback)

@@ -60,6 +60,7 @@ class BlocksparseTransformer(object):
             d = {"nt": torch.as_tensor(self.nt_lut, device=device),
                  "nn": torch.as_tensor(self.nn_lut, device=device),
                  "tn": torch.as_tensor(self.tn_lut, device=device),
+                 "nt_items": torch.as_tensor(self._luts.nt_items, device=device),
                  "mask": None}
             if self.softmax_mask_np is not None:
                 m = self.softmax_mask_np
@@ -84,6 +85,7 @@ class BlocksparseTransformer(object):
         d = self._device_luts(a.device)
         rc = lib.bst_nt(_lib.dtype_code(a.dtype), _lib.dtype_code(c_dtype), self.blk_size,
                         d["nt"].data_ptr(), self.lut_heads, self.blocks,
+                        d["nt_items"].data_ptr(), int(self._luts.nt_items.shape[1]),
                         a.data_ptr(), b.data_ptr(), c.data_ptr(),
                         batch, self.heads, hs, self.ctx_blks_q, self.ctx_blks_k, flags, _lib.stream_ptr())
         _lib.check(rc, "bst_nt")

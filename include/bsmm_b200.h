@@ -131,9 +131,13 @@ int bsmm_gate_grad(int dtype, int bsize, int blocks, const void* dw, const void*
  *   a: (batch, ctx_blks_a*bsize, heads*head_state), b: (batch, ctx_blks_b*bsize, heads*head_state)
  *   c: (batch, heads, blocks, bsize, bsize) of c_dtype.
  *   nt_lut: int32 [lut_heads][blocks][2]; lut_heads in {1, heads}.
+ *   nt_items / n_items: optional schedule for the tcgen05 kernel (blocksparse_b200/lut.py:build_nt_items, device
+ *     int32 [lut_heads][n_items][8] = (k_blk, n_valid, blk0, q0, blk1, q1, 0, 0): blocks sharing a key block, two
+ *     at a time); NULL selects the CUDA-core kernel.
  */
 int bst_nt(int dtype, int c_dtype, int bsize,
            const int32_t* nt_lut, int lut_heads, int blocks,
+           const int32_t* nt_items, int n_items,
            const void* a, const void* b, void* c,
            int batch, int heads, int head_state, int ctx_blks_a, int ctx_blks_b,
            int flags, void* stream);

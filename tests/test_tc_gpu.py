@@ -131,3 +131,64 @@ def test_tc_updat_matches_oracle(case, dtype, axis):
     mx, l2 = ref_errors(dwg.cpu().numpy(), ref * gate.cpu().numpy()[:, None, None])
     assert l2 <= 1e-5, "gated l2 %.3e" % l2
     assert _lib.device_error() == 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# block-sparse transformer GEMMs on tcgen05 (block size 64)
+from blocksparse_b200 import BlocksparseTransformer          # noqa: E402
+from oracle.bst_oracle import TransformerOracle               # noqa: E402
+
+
+def _bst_layout(rng, heads_l, qb, kb, density):
+    lay = (rng.random((heads_l, qb, kb)) < density).astype(np.int32)
+    for h in range(heads_l):
+        for q in range(qb):
+            lay[h, q, (q + h) % kb] = 1
+    # equal block count across heads (reference requirement): top up the sparser heads
+    target = int(lay.reshape(heads_l, -1).sum(1).max())
+    for h in range(heads_l):
+        free = np.argwhere(lay[h] == 0)
+        rng.shuffle(free)
+        for q, k in free[: target - int(lay[h].sum())]:
+            lay[h, q, k] = 1
+    return lay
+
+
+BST_CASES = [
+    # lut_heads, heads, q_blks, k_blks, density, head_state, batch
+    (1, 2, 4, 4, 0.6, 64, 2),
+    (1, 3, 5, 7, 0.4, 64, 1),        # rectangular, odd number of blocks per key column
+    (2, 2, 6, 5, 0.5, 128, 2),       # per-head layouts, head_state 128 (two column atoms)
+    (1, 4, 16, 16, 0.3, 64, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", BST_CASES)
+def test_tc_bst_gemms_match_oracle(case, dtype):
+    lh, heads, qb, kb, density, hs, batch = case
+    rng = np.random.default_rng(lh * 100 + heads * 10 + qb)
+    lay = _bst_layout(rng, lh, qb, kb, density)
+    bst = BlocksparseTransformer(lay if lh > 1 else lay[0], 64, heads=heads)
+    orc = TransformerOracle(lay if lh > 1 else lay[0], 64, heads=heads)
+    S = heads * hs
+    mk = lambda *shape: torch.as_tensor(rng.uniform(-1, 1, shape).astype(np.float32)).to(dtype)
+    Q, K, V = mk(batch, qb * 64, S), mk(batch, kb * 64, S), mk(batch, kb * 64, S)
+    DY = mk(batch, qb * 64, S)
+    P = torch.as_tensor(rng.uniform(0, 1, (batch, heads, bst.blocks, 64, 64)).astype(np.float32)).to(dtype)
+    Qn, Kn, Vn, DYn, Pn = (t.float().numpy() for t in (Q, K, V, DY, P))
+    F = _lib.FLAG_FORCE_TC
+    tol = 4e-3 if dtype == torch.bfloat16 else 1e-3
+    for c_dtype in (torch.float32, torch.bfloat16):
+        got = bst._nt(Q.cuda(), K.cuda(), c_dtype, flags=F)
+        assert _lib.device_error() == 0 and _lib.last_kernel() == "tcgen05_bst_nt"
+        mx, l2 = ref_errors(got.float().cpu().numpy(), orc.nt(Qn, Kn))
+        assert l2 <= (1e-5 if c_dtype == torch.float32 else 4e-3), "nt l2 %.3e" % l2
+    got = bst._xn(P.cuda(), V.cuda(), False, flags=F)
+    assert _lib.device_error() == 0 and _lib.last_kernel() == "tcgen05_bst_nn"
+    mx, l2 = ref_errors(got.float().cpu().numpy(), orc.nn(Pn, Vn))
+    assert l2 <= tol, "nn l2 %.3e" % l2
+    got = bst._xn(P.cuda(), DY.cuda(), True, flags=F)
+    assert _lib.device_error() == 0 and _lib.last_kernel() == "tcgen05_bst_tn"
+    mx, l2 = ref_errors(got.float().cpu().numpy(), orc.tn(Pn, DYn))
+    assert l2 <= tol, "tn l2 %.3e" % l2
