@@ -28,7 +28,7 @@ SIGNATURES = {
                         _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "bsmm_gate_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "bst_nt": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "bst_xn": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "bst_xn": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "bst_softmax": (_i, [_i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
     "bst_softmax_grad": (_i, [_i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
     "bst_autoregressive_mask": (_i, [_i, _vp, _i, _i, _vp, _vp, _i, _vp]),

@@ -178,7 +178,7 @@ int bst_nt(int dtype, int c_dtype, int bsize,
 }
 
 int bst_xn(int a_dtype, int dtype, int bsize, int transpose_a,
-           const int32_t* lut, int lut_heads, int blocks, int max_lut,
+           const int32_t* lut, const int32_t* out_order, int lut_heads, int blocks, int max_lut,
            const void* a, const void* b, void* c,
            int batch, int heads, int head_state, int ctx_blks_b, int ctx_blks_c,
            int flags, void* stream) {
@@ -187,7 +187,7 @@ int bst_xn(int a_dtype, int dtype, int bsize, int transpose_a,
   cudaStream_t s = (cudaStream_t)stream;
 
   if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
-    int rc = tc_bst_xn(a_dtype, dtype, bsize, transpose_a, lut, lut_heads, blocks, max_lut, a, b, c, batch, heads,
+    int rc = tc_bst_xn(a_dtype, dtype, bsize, transpose_a, lut, out_order, lut_heads, blocks, max_lut, a, b, c, batch, heads,
                        head_state, ctx_blks_b, ctx_blks_c, s);
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC) return fail(BSMM_E_ARG, "bst_xn: no tcgen05 kernel for this configuration (%s)", err_buf());

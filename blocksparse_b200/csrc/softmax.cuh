@@ -72,7 +72,7 @@ template <int BS> struct SoftmaxMap {
   static constexpr int EPL = BS / LPR;                  // elements per lane: 8, 8, 4, 2
   static constexpr int RP = 32 / LPR;                   // rows per pass: 4, 8, 8, 8
   static constexpr int GROUPS = BS / RP;                // passes per query block
-  static constexpr int KEEP = (EPL >= 8) ? 8 : 16;      // key blocks of a row kept in registers
+  static constexpr int KEEP = (EPL >= 8) ? 4 : 8;       // key blocks of a row kept in registers (more costs occupancy: measured)
 };
 
 template <typename T, int EPL> __device__ __forceinline__ void load_vec(const T* p, float (&f)[EPL]) {
@@ -158,53 +158,51 @@ bst_softmax_kernel(const SoftmaxParams p) {
     }
   };
 
-  float keep[KEEP][EPL];
-  float m = -FLT_MAX;
-#pragma unroll
-  for (int e = 0; e < KEEP; ++e) {
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) keep[e][i] = -FLT_MAX;
-    if (e < count) {
-      load_entry(e, keep[e]);
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) m = fmaxf(m, keep[e][i]);
-    }
-  }
-  for (int e = KEEP; e < count; ++e) {
-    float v[EPL]; load_entry(e, v);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) m = fmaxf(m, v[i]);
-  }
-#pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-
+  // Pass A (one read of the row): online max / sum -- (m, s) with s = sum exp(v - m), rescaled whenever m grows.
   constexpr float LOG2E = 1.4426950408889634f;
-  float s = 0.f;
+  float keep[KEEP][EPL];
+  float m = -FLT_MAX, s = 0.f;
+  auto absorb = [&](const float (&v)[EPL]) {
+    float mv = v[0];
+#pragma unroll
+    for (int i = 1; i < EPL; ++i) mv = fmaxf(mv, v[i]);
+    const float mn = fmaxf(m, mv);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) acc += exp2f((v[i] - mn) * LOG2E);
+    s = s * exp2f((m - mn) * LOG2E) + acc;
+    m = mn;
+  };
 #pragma unroll
   for (int e = 0; e < KEEP; ++e) {
-    if (e < count) {
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) { keep[e][i] = exp2f((keep[e][i] - m) * LOG2E); s += keep[e][i]; }
-    }
+    if (e < count) { load_entry(e, keep[e]); absorb(keep[e]); }
   }
+#pragma unroll 4
   for (int e = KEEP; e < count; ++e) {
     float v[EPL]; load_entry(e, v);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) s += exp2f((v[i] - m) * LOG2E);
+    absorb(v);
   }
 #pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, o);
+    const float so = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, mo);
+    s = s * exp2f((m - mn) * LOG2E) + so * exp2f((mo - mn) * LOG2E);
+    m = mn;
+  }
   const float inv = 1.f / s;
 
+  // Pass B: normalise and write (kept values from registers, the rest re-read -- L2 hits)
 #pragma unroll
   for (int e = 0; e < KEEP; ++e) {
     if (e < count) {
       int blk, kb; entry(e, blk, kb);
 #pragma unroll
-      for (int i = 0; i < EPL; ++i) keep[e][i] *= inv;
+      for (int i = 0; i < EPL; ++i) keep[e][i] = exp2f((keep[e][i] - m) * LOG2E) * inv;
       store_vec<TY, EPL>(y + (zoff + blk) * (BS * BS), keep[e]);
     }
   }
+#pragma unroll 4
   for (int e = KEEP; e < count; ++e) {
     float v[EPL]; load_entry(e, v);
     int blk, kb; entry(e, blk, kb);

@@ -168,6 +168,7 @@ tc_bst_nt_kernel(const BstNtParams p, const __grid_constant__ BstNtTmaps maps) {
 // ------------------------------------------------------------------------------------------------
 struct BstXnParams {
   const int32_t* lut;       // [lut_heads][n_out + blocks][2]
+  const int32_t* order;     // optional [lut_heads][n_out]: output blocks by decreasing LUT row length (longest first)
   long long lut_head_stride;
   int n_out, lut_heads;
   int batch, heads, blocks, head_state;
@@ -208,10 +209,11 @@ tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
     uint32_t sc = 0;
     bool alive = true;
     for (long long it = blockIdx.x; it < total && alive; it += gridDim.x) {
-      const int o = (int)(it % p.n_out);
       const int bh = (int)(it / p.n_out);
       const int b = bh / p.heads, h = bh % p.heads;
-      const int32_t* lut = p.lut + (p.lut_heads > 1 ? h : 0) * p.lut_head_stride;
+      const int hl = p.lut_heads > 1 ? h : 0;
+      const int o = p.order ? p.order[hl * p.n_out + (int)(it % p.n_out)] : (int)(it % p.n_out);
+      const int32_t* lut = p.lut + hl * p.lut_head_stride;
       const int first = lut[2 * o], count = lut[2 * o + 1];
       const int2* ent = reinterpret_cast<const int2*>(lut) + first;
       for (int e0 = 0; e0 < count && alive; e0 += 32) {
@@ -245,9 +247,10 @@ tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
     uint32_t sc = 0, n = 0;
     bool alive = true;
     for (long long it = blockIdx.x; it < total && alive; it += gridDim.x, ++n) {
-      const int o = (int)(it % p.n_out);
       const int h = (int)((it / p.n_out) % p.heads);
-      const int32_t* lut = p.lut + (p.lut_heads > 1 ? h : 0) * p.lut_head_stride;
+      const int hl = p.lut_heads > 1 ? h : 0;
+      const int o = p.order ? p.order[hl * p.n_out + (int)(it % p.n_out)] : (int)(it % p.n_out);
+      const int32_t* lut = p.lut + hl * p.lut_head_stride;
       const int count = lut[2 * o + 1];
       const uint32_t buf = n & 1;
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty[buf], ((n >> 1) & 1) ^ 1, abort_flag))) { g_tc_error = 33; break; }
@@ -277,10 +280,11 @@ tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
     const long long S = (long long)p.heads * p.head_state;
     uint32_t n = 0;
     for (long long it = blockIdx.x; it < total; it += gridDim.x, ++n) {
-      const int o = (int)(it % p.n_out);
       const int bh = (int)(it / p.n_out);
       const int b = bh / p.heads, h = bh % p.heads;
-      const int32_t* lut = p.lut + (p.lut_heads > 1 ? h : 0) * p.lut_head_stride;
+      const int hl = p.lut_heads > 1 ? h : 0;
+      const int o = p.order ? p.order[hl * p.n_out + (int)(it % p.n_out)] : (int)(it % p.n_out);
+      const int32_t* lut = p.lut + hl * p.lut_head_stride;
       const int count = lut[2 * o + 1];
       const uint32_t buf = n & 1;
       ptx::mbar_wait(&acc_full[buf], (n >> 1) & 1, abort_flag);
@@ -371,7 +375,7 @@ inline int tc_bst_nt(int dtype, int c_dtype, int bsize, const int32_t* items, in
   return check_launch("tcgen05_bst_nt");
 }
 
-inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const int32_t* lut, int lut_heads, int blocks,
+inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const int32_t* lut, const int32_t* order, int lut_heads, int blocks,
                      int max_lut, const void* a, const void* b, void* c, int batch, int heads, int head_state,
                      int ctx_blks_b, int ctx_blks_c, cudaStream_t s) {
   (void)max_lut;
@@ -383,7 +387,7 @@ inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const i
   if (int e = make_tmap_2d(&maps.a, dtype, a, 64, (uint64_t)batch * heads * blocks * 64, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   if (int e = make_tmap_2d(&maps.b, dtype, b, S, (uint64_t)batch * ctx_blks_b * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   BstXnParams p;
-  p.lut = lut; p.lut_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_c + blocks) : 0; p.n_out = ctx_blks_c; p.lut_heads = lut_heads;
+  p.lut = lut; p.order = order; p.lut_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_c + blocks) : 0; p.n_out = ctx_blks_c; p.lut_heads = lut_heads;
   p.batch = batch; p.heads = heads; p.blocks = blocks; p.head_state = head_state;
   p.ctx_rows_b = ctx_blks_b * 64; p.ctx_rows_c = ctx_blks_c * 64; p.transpose_a = transpose_a; p.c = c;
   const size_t smem = (size_t)BST_STAGES * 4 * BST_TILE;

@@ -419,6 +419,9 @@ class TransformerLuts(object):
         self.nn_lut = np.stack(nn_luts)
         self.tn_lut = np.stack(tn_luts)
         self.nt_items = build_nt_items(self.tn_list)
+        # output blocks by decreasing row length (longest first) for the persistent XN kernels
+        self.nn_order = np.stack([np.argsort(-np.array([len(r) for r in rows]), kind="stable") for rows in self.nn_list]).astype(np.int32)
+        self.tn_order = np.stack([np.argsort(-np.array([len(r) for r in rows]), kind="stable") for rows in self.tn_list]).astype(np.int32)
         self.softmax_mask = self.softmax_mask_np = None
         if mask_callback is not None:
             self.init_softmax_mask(mask_callback)

@@ -61,6 +61,8 @@ class BlocksparseTransformer(object):
                  "nn": torch.as_tensor(self.nn_lut, device=device),
                  "tn": torch.as_tensor(self.tn_lut, device=device),
                  "nt_items": torch.as_tensor(self._luts.nt_items, device=device),
+                 "nn_order": torch.as_tensor(self._luts.nn_order, device=device),
+                 "tn_order": torch.as_tensor(self._luts.tn_order, device=device),
                  "mask": None}
             if self.softmax_mask_np is not None:
                 m = self.softmax_mask_np
@@ -107,8 +109,9 @@ class BlocksparseTransformer(object):
         c = torch.empty((batch, ctx_blks_c * self.blk_size, S), dtype=b.dtype, device=b.device)
         d = self._device_luts(b.device)
         lut = d["tn"] if transpose_a else d["nn"]
+        order = d["tn_order"] if transpose_a else d["nn_order"]
         rc = lib.bst_xn(_lib.dtype_code(a.dtype), _lib.dtype_code(b.dtype), self.blk_size, int(transpose_a),
-                        lut.data_ptr(), self.lut_heads, self.blocks, self.tn_max if transpose_a else self.nn_max,
+                        lut.data_ptr(), order.data_ptr(), self.lut_heads, self.blocks, self.tn_max if transpose_a else self.nn_max,
                         a.data_ptr(), b.data_ptr(), c.data_ptr(),
                         batch, self.heads, hs, ctx_blks_b, ctx_blks_c, flags, _lib.stream_ptr())
         _lib.check(rc, "bst_xn")

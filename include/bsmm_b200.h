@@ -146,9 +146,11 @@ int bst_nt(int dtype, int c_dtype, int bsize,
  * XN: transpose_a=0 (NN): C[b, q-blk, h, :] = sum_{(blk,k) in lut[q]} A[b,h,blk]   . B[b, k-blk, h, :]
  *     transpose_a=1 (TN): C[b, k-blk, h, :] = sum_{(blk,q) in lut[k]} A[b,h,blk]^T . B[b, q-blk, h, :]
  *   lut: int32 [lut_heads][ctx_blks_c + blocks][2] -- the reference's nn_lut / tn_lut verbatim.
+ *   out_order: optional int32 [lut_heads][ctx_blks_c], output blocks sorted by decreasing LUT row length; the
+ *     persistent tcgen05 kernel walks it so that long rows (e.g. strided attention columns) start first.
  */
 int bst_xn(int a_dtype, int dtype, int bsize, int transpose_a,
-           const int32_t* lut, int lut_heads, int blocks, int max_lut,
+           const int32_t* lut, const int32_t* out_order, int lut_heads, int blocks, int max_lut,
            const void* a, const void* b, void* c,
            int batch, int heads, int head_state, int ctx_blks_b, int ctx_blks_c,
            int flags, void* stream);
