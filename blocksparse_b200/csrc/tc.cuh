@@ -120,7 +120,6 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   uint8_t* sO = smem + XS * STAGE_BYTES;          // STG x XBYTES staging for the output tile
   __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty;
   __shared__ __align__(16) int4 cmd[XS][8];       // per run: (B descriptor low word for K slice 0, D tmem address, idesc, accumulate)
-  __shared__ int cmd_n[XS];                       // number of runs
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   volatile int* abort_flag = &abort_s;
@@ -175,9 +174,9 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         if (lane >= 12 && lane < 12 + n_runs) {
           const uint32_t r0 = (uint32_t)cur;
           cmd[st][lane - 12] = make_int4((int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (r0 & 0xffffu)),
-                                         (int)(tmem + (r0 >> 16)), (int)(p_idesc0 | (r1 & ~1u)), (int)(r1 & 1u));
+                                         (int)(tmem + (r0 >> 16)), (int)(p_idesc0 | (r1 & ~1u)),
+                                         (int)((r1 & 1u) | (lane == 12 ? (uint32_t)n_runs << 8 : 0u)));
         }
-        if (lane == 0) cmd_n[st] = n_runs;
         __syncwarp();
         uint8_t* stage = sStage + st * STAGE_BYTES;
         if (lane == 0) {
@@ -217,14 +216,19 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         const uint32_t st = gc % XS;
         if (!__all_sync(0xffffffffu, ptx::mbar_wait(&full[st], (gc / XS) & 1, abort_flag))) { g_tc_error = 4; alive = false; break; }
         ptx::tc_fence_after();
-        const int n_runs = cmd_n[st];
         if (ptx::elect_one()) {
           const uint64_t a_st = a_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
-          // all run commands of the group in registers first (independent LDS.128s), then straight-line
-          // issue: run 0 fills the A collector, runs 1.. reuse it
+          // Commands go to registers first (independent LDS.128s), then straight-line issue: run 0 fills the A
+          // collector, runs 1.. reuse it.  Most groups have <= 4 runs, so only 4 commands are fetched eagerly;
+          // the run count rides in the first command.
           int4 c[8];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) c[r] = cmd[st][r];
+          for (int r = 0; r < 4; ++r) c[r] = cmd[st][r];
+          const int n_runs = c[0].w >> 8;
+          if (n_runs > 4) {
+#pragma unroll
+            for (int r = 4; r < 8; ++r) c[r] = cmd[st][r];
+          }
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
             const uint64_t adesc = a_st + (uint64_t)(ks * a_kstep16);
@@ -232,7 +236,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             for (int r = 0; r < 8; ++r) {
               if (r >= n_runs) break;              // a real (uniform) branch: skipped runs cost nothing
               const uint64_t bdesc = ((uint64_t)b_desc_hi << 32) | (uint32_t)((uint32_t)c[r].x + ks * b_kstep16);
-              const uint32_t acc = (ks > 0) ? 1u : (uint32_t)c[r].w;
+              const uint32_t acc = (ks > 0) ? 1u : ((uint32_t)c[r].w & 1u);
               if (r == 0) ptx::mma_ss_a_fill((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
               else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
             }
