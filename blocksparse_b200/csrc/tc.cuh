@@ -440,7 +440,7 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   p.groups_off = sched_groups_off;
   const int tile_blocks = sched_tile_blocks;
   const int occ = (tile_blocks * bsize <= 256) ? 2 : 1;      // half-width tiles run two CTAs per SM
-  if (p.n_ktiles <= 0 || tile_blocks <= 0 || tile_blocks > 512 / bsize || p.n_ktiles * tile_blocks < n_out ||
+  if (p.n_ktiles <= 0 || tile_blocks <= 0 || tile_blocks > 512 / bsize || (long long)p.n_ktiles * tile_blocks < n_out ||
       sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
     return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
                 p.n_ktiles, tile_blocks, n_out);

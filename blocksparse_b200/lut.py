@@ -166,10 +166,10 @@ class MatmulLuts(object):
     def updat_schedule(self, bsize, k_per_tile=None):
         return build_updat_schedule(self.updat_lut, self.CB, self.KB, bsize, k_per_tile)
 
-    def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8):
+    def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None):
         outs, ins, wids = self._b if bprop else self._f
         n_out = self.CB if bprop else self.KB
-        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group)
+        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group, n_tiles)
 
 
 GROUP_INTS = 32          # one 128-byte record per schedule group (one coalesced warp load)
@@ -177,7 +177,28 @@ GROUP_MAX_W = 8          # W blocks per group record (ints 4..11)
 GROUP_MAX_RUNS = 8       # MMA runs per group record (ints 12..27, two ints each)
 
 
-def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per_group=8):
+def pick_tile_count(n_out, n_ntiles, cta_slots, max_blocks_per_tile):
+    """Number of output tiles along the feature axis for the persistent xprop kernel.
+
+    The kernel runs `cta_slots` CTAs (SMs x CTAs per SM) over n_ntiles * n_ktiles tiles, so the tile count should
+    land just under a multiple of cta_slots (512 tiles on 296 slots waste 14 % in the second wave).  Among the tile
+    counts that keep tiles <= max_blocks_per_tile blocks wide we take the one with the least idle slot-time,
+    preferring wider tiles (more reuse of each activation tile) on ties.
+    """
+    lo = ceil_div(n_out, max_blocks_per_tile)
+    best = None
+    for n_kt in range(lo, min(n_out, 2 * lo) + 1):
+        tiles = n_ntiles * n_kt
+        waves = ceil_div(tiles, cta_slots)
+        # time ~ waves * (average tile width + a fixed per-tile cost worth ~1.5 blocks: narrower tiles re-stage
+        # more activation tiles per output block)
+        cost = waves * (n_out / float(n_kt) + 1.5)
+        if best is None or cost < best[0]:
+            best = (cost, n_kt)
+    return best[1]
+
+
+def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None):
     """Schedule for the tcgen05 xprop kernel (csrc/tc.cuh).
 
     An output tile covers `blocks_per_tile` consecutive output blocks (their fp32 accumulators live
@@ -206,15 +227,21 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     """
     T = int(blocks_per_tile)
     assert 1 <= w_per_group <= GROUP_MAX_W
-    n_tiles = ceil_div(n_out, T)
+    if n_tiles is None:
+        n_tiles = ceil_div(n_out, T)
+    n_tiles = int(n_tiles)
+    assert n_tiles * T >= n_out
+    # tile t covers output blocks [bounds[t], bounds[t+1]): sizes differ by at most one block
+    bounds = (np.arange(n_tiles + 1, dtype=np.int64) * n_out) // n_tiles
+    assert int(np.diff(bounds).max()) <= T
     outs = np.asarray(outs, dtype=np.int64)
     ins = np.asarray(ins, dtype=np.int64)
     wids = np.asarray(wids, dtype=np.int64)
     nnz = len(outs)
-    tile = outs // T
+    tile = np.searchsorted(bounds, outs, side="right") - 1
     order = np.lexsort((outs, ins, tile))          # by tile, then input block, then slot
     tile_s, ins_s, outs_s, w_s = tile[order], ins[order], outs[order], wids[order]
-    slot_s = outs_s - tile_s * T
+    slot_s = outs_s - bounds[tile_s]
 
     # position of each pair inside its (tile, in_block) cluster -> chunk of w_per_group pairs = group
     new_cluster = np.ones(nnz, dtype=bool)
@@ -251,7 +278,7 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     groups_per_tile = np.bincount(tile_s[g_first], minlength=n_tiles)
     tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
     touched = np.zeros(n_tiles, dtype=np.int64)
-    np.bitwise_or.at(touched, tile, np.int64(1) << (outs - tile * T))
+    np.bitwise_or.at(touched, tile, np.int64(1) << (outs - bounds[tile]))
 
     hdr_ints = 4 + 4 * n_tiles
     grp_off = ceil_div(hdr_ints, GROUP_INTS) * GROUP_INTS
@@ -260,8 +287,8 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     th = sched[4:hdr_ints].reshape(n_tiles, 4)
     th[:, 0] = tile_first_group
     th[:, 1] = groups_per_tile
-    th[:, 2] = np.arange(n_tiles) * T
-    th[:, 3] = np.minimum(T, n_out - np.arange(n_tiles) * T) | (touched << 8)
+    th[:, 2] = bounds[:-1]
+    th[:, 3] = np.diff(bounds) | (touched << 8)
     gr = sched[grp_off:].reshape(n_groups, GROUP_INTS)
     gr[:, 0] = ins_s[g_first]
     gr[:, 1] = g_count | (runs_per_group << 8)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lut import MatmulLuts
+from .lut import MatmulLuts, pick_tile_count
 
 # tcgen05 tile width (output blocks whose accumulators share one CTA's tensor memory)
 import os
@@ -120,13 +120,8 @@ class BlocksparseMatMul(object):
             }
             tb = _TILE_BLOCKS.get(self.bsize)
             if tb:
-                wpg = _W_PER_GROUP[self.bsize]
-                fs, foff = self._luts.tile_schedule(False, tb, self.bsize, wpg)
-                bs_, boff = self._luts.tile_schedule(True, tb, self.bsize, wpg)
-                d["fprop_sched"] = torch.as_tensor(fs, device=device)
-                d["bprop_sched"] = torch.as_tensor(bs_, device=device)
-                d["sched_tiles_f"], d["sched_tiles_b"], d["tile_blocks"] = int(fs[0]), int(bs_[0]), tb
-                d["sched_off_f"], d["sched_off_b"] = foff, boff
+                d["xprop_sched"] = {}          # (bprop, n_tiles) -> (tensor, n_tiles, groups_off), built on demand
+                d["cta_slots"] = torch.cuda.get_device_properties(device).multi_processor_count * (2 if _HALF else 1)
                 us, uoff = self._luts.updat_schedule(self.bsize)
                 d["updat_sched"] = torch.as_tensor(us, device=device)
                 d["updat_tiles"], d["updat_kt"] = int(us[0]), int(us[2])
@@ -155,7 +150,16 @@ class BlocksparseMatMul(object):
         N = x2.shape[1] if self.axis == 0 else x2.shape[0]
         d = self._device_luts(x.device)
         lut = d["bprop" if bprop else "fprop"]
-        sched = d.get("bprop_sched" if bprop else "fprop_sched")
+        sched, sched_tiles, sched_off = None, 0, 0
+        if "xprop_sched" in d:
+            # tile count chosen so that (minibatch tiles) x (feature tiles) fills whole waves of the persistent grid
+            tb = _TILE_BLOCKS[self.bsize]
+            n_kt = pick_tile_count(n_out, -(-N // 128), d["cta_slots"], tb)
+            key = (bool(bprop), n_kt)
+            if key not in d["xprop_sched"]:
+                arr, off = self._luts.tile_schedule(bprop, tb, self.bsize, _W_PER_GROUP[self.bsize], n_tiles=n_kt)
+                d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off)
+            sched, sched_tiles, sched_off = d["xprop_sched"][key]
         y2 = torch.empty((feat_out, N) if self.axis == 0 else (N, feat_out), dtype=x.dtype, device=x.device)
         if gate is not None:
             gate = gate.to(torch.float32).contiguous()
@@ -163,8 +167,7 @@ class BlocksparseMatMul(object):
                             lut.data_ptr(), n_out, n_in, self.blocks,
                             x2.data_ptr(), w.data_ptr(), y2.data_ptr(), N,
                             _lib.ptr(gate),
-                            _lib.ptr(sched), d.get("sched_tiles_b" if bprop else "sched_tiles_f", 0), d.get("tile_blocks", 0),
-                            d.get("sched_off_b" if bprop else "sched_off_f", 0),
+                            _lib.ptr(sched), sched_tiles, _TILE_BLOCKS.get(self.bsize, 0), sched_off,
                             flags, _lib.stream_ptr())
         _lib.check(rc, "bsmm_xprop")
         if self.axis == 0:

@@ -98,10 +98,12 @@ def test_tile_schedule_is_a_faithful_regrouping(bsize, T, wpg):
             wbytes16 = (bsize * bsize * 2) >> 4
             seen = set()
             gi_expected = 0
+            fo_expected = 0
             for t in range(n_tiles):
                 fg, ng, fo, packed = s[4 + 4 * t: 8 + 4 * t]
                 no, mask = packed & 0xff, packed >> 8
-                assert fg == gi_expected and fo == t * T and no == min(T, n_out - fo)
+                assert fg == gi_expected and fo == fo_expected and 1 <= no <= T       # contiguous tiles, at most T wide
+                fo_expected += no
                 assert mask == sum(1 << sl for sl in range(no) if lists[fo + sl])
                 gi_expected += ng
                 touched = set()
@@ -129,7 +131,7 @@ def test_tile_schedule_is_a_faithful_regrouping(bsize, T, wpg):
                             touched.add(col // bsize + i)
                         covered += n // bsize
                     assert covered == n_w
-            assert len(seen) == L.blocks and gi_expected == n_groups
+            assert len(seen) == L.blocks and gi_expected == n_groups and fo_expected == n_out
 
 
 def _cb(name, has_mask):
@@ -200,3 +202,19 @@ def test_updat_schedule_covers_every_block_once(bsize):
             for sl in range(n_act, KT):
                 assert (rec[t, [16 + i * KT + sl for i in range(G)]] == -1).all()
         assert len(seen) == L.blocks
+
+
+def test_pick_tile_count_fills_whole_waves():
+    from blocksparse_b200.lut import pick_tile_count
+    # BASELINE cfg 2 on a B200 with two CTAs per SM: 32 minibatch tiles, 128 output blocks, 296 CTA slots
+    n_kt = pick_tile_count(128, 32, 296, 8)
+    assert n_kt == 18 and 32 * n_kt <= 2 * 296            # 576 tiles: two full waves instead of 512 in 1.73
+    assert pick_tile_count(8, 1, 296, 8) == 2             # idle slots: narrower tiles spread a small problem over more CTAs
+    for n_out, n_nt in [(5, 3), (128, 1), (37, 200), (1, 1)]:
+        k = pick_tile_count(n_out, n_nt, 296, 8)
+        assert -(-n_out // k) <= 8 and k >= -(-n_out // 8)
+    # uneven tiles cover every block exactly once
+    L = MatmulLuts((np.random.default_rng(0).random((40, 37)) < 0.3).astype(np.int32) | np.eye(40, 37, dtype=np.int32))
+    s, off = L.tile_schedule(False, 8, 32, 8, n_tiles=6)
+    sizes = [int(s[4 + 4 * t + 3]) & 0xff for t in range(6)]
+    assert sum(sizes) == 37 and max(sizes) - min(sizes) <= 1
