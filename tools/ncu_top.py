@@ -16,7 +16,7 @@ for r in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; idx = {k: i for i, k in enumerate(h)}
-data = [r for r in rows[2:] if len(r) == len(h)]
+data = [r for r in rows[2:] if len(r) == len(h) and r[idx['# Samples']].isdigit()]
 stalls = [k for k in h if k.startswith('stall_') and 'Not Issued' not in k]
 tot = sum(int(r[idx['# Samples']] or 0) for r in data)
 print("stall sampling, first kernel instance: %d samples; hottest SASS lines:" % tot)
