@@ -74,6 +74,55 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   }
 }
 
+// Hide a value's provenance from the optimiser (otherwise it re-materialises shared-window addresses at every use).
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+// Address-based variants: shared-window addresses on sm_100 embed the CTA rank (S2UR SR_CgaCtaId + LEA per cvta),
+// so hot loops convert a barrier array's base ONCE and index it arithmetically.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (mbar_try_wait_a(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait_a(bar, parity)) return true;
+    if (abort_flag && *abort_flag) return false;
+    if (globaltimer_ns() - t0 > 500000000ull) {
+      if (abort_flag) *abort_flag = 1;
+      return false;
+    }
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, int a, int b, int c, int d) {
+  asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // ---- TMA ---------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

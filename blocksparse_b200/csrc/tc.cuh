@@ -66,7 +66,13 @@ inline int make_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t in
 // OCC = CTAs per SM.  OCC 2 halves the output tile (256 TMEM columns, 8/4 blocks) so that two CTAs --
 // two independent MMA-issuing threads -- share one SM's tensor core: the issue rate of one thread
 // (~45 cycles per N=32 MMA, profiles/r1_xprop_v3_ncu.txt) is what bounds the single-CTA kernel.
-template <int BS, int OCC> struct XpropCfg;
+// VAR 1 = "sparse" variant for layouts with ~1 W block per group (density <= ~12 %): 2 W slots per stage instead of
+// 8, which doubles the number of stages in flight -- at 5-10 % density the kernel is bound by the TMA round trip.
+template <int BS, int OCC, int VAR = 0> struct XpropCfg;
+template <> struct XpropCfg<32, 2, 1> {
+  static constexpr int XS = 6, WPS = 2, STG = 4, TCOLS = 256;
+  static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
+};
 template <> struct XpropCfg<32, 1> {
   static constexpr int XS = 6, WPS = 8, STG = 8, TCOLS = 512;  // group stages, W slots per stage, staging buffers, TMEM columns
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;     // 64-byte rows
@@ -105,10 +111,10 @@ struct XpropTcParams {
 };
 struct XpropTmaps { CUtensorMap x, w, y; };
 
-template <int BS, bool BF16, int OCC>
+template <int BS, bool BF16, int OCC, int VAR = 0>
 __global__ void __launch_bounds__(XPROP_THREADS, OCC)
 tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) {
-  using Cfg = XpropCfg<BS, OCC>;
+  using Cfg = XpropCfg<BS, OCC, VAR>;
   constexpr int XS = Cfg::XS, WPS = Cfg::WPS, STG = Cfg::STG;
   constexpr int KS = BS / 16;                     // K=16 slices per block
   constexpr uint32_t XBYTES = 128 * BS * 2, WBYTES = BS * BS * 2;
@@ -149,6 +155,8 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     uint32_t gbase = 0;                   // groups of earlier tiles
     bool alive = true;
     const uint32_t p_idesc0 = ptx::make_idesc_f16(BF16, p.axis0 != 0, !p.bprop, 128, 0);
+    const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
+                   cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0])), stage0 = ptx::opaque(ptx::smem_u32(sStage));
     const uint32_t p_bdesc_lo = (uint32_t)ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
       const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
@@ -167,29 +175,30 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         const int in_blk = __shfl_sync(0xffffffffu, cur, 0);
         const int counts = __shfl_sync(0xffffffffu, cur, 1);
         const int n_w = counts & 0xff, n_runs = counts >> 8;
-        if (!__all_sync(0xffffffffu, ptx::mbar_wait(&empty[st], ((gc / XS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(empty0 + st * 8, ((gc / XS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
         // lanes 12..19 hold int0 of run (lane-12); int1 sits 8 lanes up.  They write the ready-to-issue
         // command so the issuing thread only moves registers.
         const uint32_t r1 = (uint32_t)__shfl_down_sync(0xffffffffu, cur, 8);
         if (lane >= 12 && lane < 12 + n_runs) {
           const uint32_t r0 = (uint32_t)cur;
-          cmd[st][lane - 12] = make_int4((int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (r0 & 0xffffu)),
-                                         (int)(tmem + (r0 >> 16)), (int)(p_idesc0 | (r1 & ~1u)),
-                                         (int)((r1 & 1u) | (lane == 12 ? (uint32_t)n_runs << 8 : 0u)));
+          ptx::st_shared_v4(cmd0 + st * (8 * 16) + (lane - 12) * 16,
+                            (int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (r0 & 0xffffu)),
+                            (int)(tmem + (r0 >> 16)), (int)(p_idesc0 | (r1 & ~1u)),
+                            (int)((r1 & 1u) | (lane == 12 ? (uint32_t)n_runs << 8 : 0u)));
         }
         __syncwarp();
-        uint8_t* stage = sStage + st * STAGE_BYTES;
+        const uint32_t stage = stage0 + st * STAGE_BYTES, fbar = full0 + st * 8;
         if (lane == 0) {
-          ptx::mbar_expect_tx(&full[st], XBYTES + (uint32_t)n_w * WBYTES);
+          ptx::mbar_expect_tx_a(fbar, XBYTES + (uint32_t)n_w * WBYTES);
           if (!p.axis0) {
-            ptx::tma_load_2d(stage, &maps.x, &full[st], in_blk * BS, nt * 128);          // [128 n][bs c], K-major A
-          } else {                                                                      // [bs c][128 n] as two 64-wide boxes, MN-major A
-            ptx::tma_load_2d(stage, &maps.x, &full[st], nt * 128, in_blk * BS);
-            ptx::tma_load_2d(stage + XBYTES / 2, &maps.x, &full[st], nt * 128 + 64, in_blk * BS);
+            ptx::tma_load_2d_a(stage, &maps.x, fbar, in_blk * BS, nt * 128);          // [128 n][bs c], K-major A
+          } else {                                                                   // [bs c][128 n] as two 64-wide boxes, MN-major A
+            ptx::tma_load_2d_a(stage, &maps.x, fbar, nt * 128, in_blk * BS);
+            ptx::tma_load_2d_a(stage + XBYTES / 2, &maps.x, fbar, nt * 128 + 64, in_blk * BS);
           }
         }
         if (lane >= 4 && lane < 4 + n_w)
-          ptx::tma_load_2d(stage + XBYTES + (lane - 4) * WBYTES, &maps.w, &full[st], 0, cur * BS);
+          ptx::tma_load_2d_a(stage + XBYTES + (lane - 4) * WBYTES, &maps.w, fbar, 0, cur * BS);
         __syncwarp();
       }
       gbase += n_groups;
@@ -205,6 +214,8 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
                                      : ptx::make_smem_desc(ptx::smem_u32(sStage), 16, Cfg::SBO, Cfg::SWZ);
     const uint32_t a_kstep16 = p.axis0 ? (16u * 128u) >> 4 : 2u;
     const uint32_t b_desc_hi = (uint32_t)(ptx::make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) >> 32);
+    const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
+                   cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0]));
     uint32_t gc = 0, tile_it = 0;
     bool alive = true;
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x, ++tile_it) {
@@ -214,7 +225,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       ptx::tc_fence_after();
       for (int g = 0; g < n_groups; ++g, ++gc) {
         const uint32_t st = gc % XS;
-        if (!__all_sync(0xffffffffu, ptx::mbar_wait(&full[st], (gc / XS) & 1, abort_flag))) { g_tc_error = 4; alive = false; break; }
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(full0 + st * 8, (gc / XS) & 1, abort_flag))) { g_tc_error = 4; alive = false; break; }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t a_st = a_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
@@ -222,12 +233,15 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
           // collector, runs 1.. reuse it.  Most groups have <= 4 runs, so only 4 commands are fetched eagerly;
           // the run count rides in the first command.
           int4 c[8];
+          const uint32_t cq = cmd0 + st * (8 * 16);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) c[r] = cmd[st][r];
+          for (int r = 0; r < 4; ++r)
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r].z), "=r"(c[r].w) : "r"(cq + r * 16));
           const int n_runs = c[0].w >> 8;
           if (n_runs > 4) {
 #pragma unroll
-            for (int r = 4; r < 8; ++r) c[r] = cmd[st][r];
+            for (int r = 4; r < 8; ++r)
+              asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r].z), "=r"(c[r].w) : "r"(cq + r * 16));
           }
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
@@ -241,7 +255,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
               else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
             }
           }
-          ptx::tc_commit(&empty[st]);       // the stage is free once these MMAs retire
+          ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
         }
         __syncwarp();
       }
@@ -379,16 +393,16 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   if (warp == XPROP_PRODUCERS) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int BS, int OCC>
+template <int BS, int OCC, int VAR = 0>
 constexpr size_t xprop_smem_bytes() {
-  using Cfg = XpropCfg<BS, OCC>;
+  using Cfg = XpropCfg<BS, OCC, VAR>;
   return (size_t)Cfg::XS * (128 * BS * 2 + Cfg::WPS * BS * BS * 2) + (size_t)Cfg::STG * 128 * BS * 2;
 }
 
-template <int BS, bool BF16, int OCC>
+template <int BS, bool BF16, int OCC, int VAR = 0>
 int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count, cudaStream_t s) {
-  auto kern = tc_xprop_kernel<BS, BF16, OCC>;
-  constexpr size_t smem = xprop_smem_bytes<BS, OCC>();
+  auto kern = tc_xprop_kernel<BS, BF16, OCC, VAR>;
+  constexpr size_t smem = xprop_smem_bytes<BS, OCC, VAR>();
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -438,12 +452,19 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   // the schedule itself lives in device memory; its shape is passed by value
   p.n_ktiles = sched_tiles;
   p.groups_off = sched_groups_off;
-  const int tile_blocks = sched_tile_blocks;
+  const int tile_blocks = sched_tile_blocks & 0xff;
+  const int w_per_group = sched_tile_blocks >> 8;          // 0 = the default of the tile width
   const int occ = (tile_blocks * bsize <= 256) ? 2 : 1;      // half-width tiles run two CTAs per SM
   if (p.n_ktiles <= 0 || tile_blocks <= 0 || tile_blocks > 512 / bsize || (long long)p.n_ktiles * tile_blocks < n_out ||
       sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
     return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
                 p.n_ktiles, tile_blocks, n_out);
+  if (w_per_group != 0 && !(bsize == 32 && occ == 2 && w_per_group == 2) &&
+      w_per_group != (bsize == 32 ? 8 : (occ == 2 ? 2 : 4)))
+    return fail(BSMM_E_ARG, "bsmm_xprop: schedule built with %d W blocks per group, no kernel variant matches", w_per_group);
+  if (occ == 2 && bsize == 32 && w_per_group == 2)
+    return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 1>(p, maps, dev.sm_count, s)
+                              : launch_tc_xprop<32, false, 2, 1>(p, maps, dev.sm_count, s);
   if (occ == 2) {
     if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2>(p, maps, dev.sm_count, s)
                                                : launch_tc_xprop<32, false, 2>(p, maps, dev.sm_count, s);

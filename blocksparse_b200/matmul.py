@@ -155,11 +155,17 @@ class BlocksparseMatMul(object):
             # tile count chosen so that (minibatch tiles) x (feature tiles) fills whole waves of the persistent grid
             tb = _TILE_BLOCKS[self.bsize]
             n_kt = pick_tile_count(n_out, -(-N // 128), d["cta_slots"], tb)
+            # sparse layouts (about one W block per group) use 2 W slots per stage => twice the stages in flight
+            wpg = _W_PER_GROUP[self.bsize]
+            sparse = _HALF and self.bsize == 32 and self.blocks * tb <= 1.0 * self.CB * self.KB
+            if sparse:
+                wpg = 2
             key = (bool(bprop), n_kt)
             if key not in d["xprop_sched"]:
-                arr, off = self._luts.tile_schedule(bprop, tb, self.bsize, _W_PER_GROUP[self.bsize], n_tiles=n_kt)
+                arr, off = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt)
                 d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off)
             sched, sched_tiles, sched_off = d["xprop_sched"][key]
+            tile_arg = tb | ((wpg << 8) if sparse else 0)
         y2 = torch.empty((feat_out, N) if self.axis == 0 else (N, feat_out), dtype=x.dtype, device=x.device)
         if gate is not None:
             gate = gate.to(torch.float32).contiguous()
@@ -167,7 +173,7 @@ class BlocksparseMatMul(object):
                             lut.data_ptr(), n_out, n_in, self.blocks,
                             x2.data_ptr(), w.data_ptr(), y2.data_ptr(), N,
                             _lib.ptr(gate),
-                            _lib.ptr(sched), sched_tiles, _TILE_BLOCKS.get(self.bsize, 0), sched_off,
+                            _lib.ptr(sched), sched_tiles, tile_arg if sched is not None else 0, sched_off,
                             flags, _lib.stream_ptr())
         _lib.check(rc, "bsmm_xprop")
         if self.axis == 0:

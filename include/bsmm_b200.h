@@ -91,7 +91,8 @@ int         bsmm_device_error(void);
  *    zero-filled (reference behaviour, cn_64.cu:243-253).
  * sched: optional tile schedule for the tcgen05 kernels built by the host layer
  *    (blocksparse_b200/lut.py:build_tile_schedule, device memory) with its shape passed by value:
- *    sched_tiles output tiles of sched_tile_blocks consecutive output blocks each, group records
+ *    sched_tiles output tiles of (sched_tile_blocks & 0xff) consecutive output blocks each (bits 8.. = W blocks
+ *    per schedule group when it differs from the default, selecting the deep-pipeline "sparse" variant), group records
  *    starting at int32 index sched_groups_off; NULL selects the CUDA-core kernels.
  * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).
  */
