@@ -216,19 +216,19 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     const uint32_t b_desc_hi = (uint32_t)(ptx::make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) >> 32);
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
                    cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0]));
-    uint32_t gc = 0, tile_it = 0;
+    uint32_t st = 0, ph = 0, tile_it = 0;          // pipeline stage and its phase bit, advanced incrementally
+    const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
     bool alive = true;
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x, ++tile_it) {
       const int kt = t % p.n_ktiles;
       const int n_groups = sched[4 + 4 * kt + 1];
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, (tile_it & 1) ^ 1, abort_flag))) { g_tc_error = 3; break; }
       ptx::tc_fence_after();
-      for (int g = 0; g < n_groups; ++g, ++gc) {
-        const uint32_t st = gc % XS;
-        if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(full0 + st * 8, (gc / XS) & 1, abort_flag))) { g_tc_error = 4; alive = false; break; }
+      for (int g = 0; g < n_groups; ++g) {
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(full0 + st * 8, ph, abort_flag))) { g_tc_error = 4; alive = false; break; }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint64_t a_st = a_desc0 + (uint64_t)((st * STAGE_BYTES) >> 4);
+          const uint32_t a_lo = a_lo0 + st * (STAGE_BYTES >> 4);
           // Commands go to registers first (independent LDS.128s), then straight-line issue: run 0 fills the A
           // collector, runs 1.. reuse it.  Most groups have <= 4 runs, so only 4 commands are fetched eagerly;
           // the run count rides in the first command.
@@ -245,7 +245,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
           }
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t adesc = a_st + (uint64_t)(ks * a_kstep16);
+            const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint32_t)(a_lo + ks * a_kstep16);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
               if (r >= n_runs) break;              // a real (uniform) branch: skipped runs cost nothing
@@ -258,6 +258,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
           ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
         }
         __syncwarp();
+        if (++st == XS) { st = 0; ph ^= 1; }
       }
       if (ptx::elect_one()) ptx::tc_commit(&acc_full);
       __syncwarp();
