@@ -152,30 +152,39 @@ bst_softmax_kernel(const SoftmaxParams p) {
     if (mask) {
       uint64_t w = (uint64_t)mask[(long long)blk * BS];
       if (p.autoregress_at_key >= 0) w = autoregress_word<BS>(w, p.autoregress_at_key, kb, q * BS + row);
-      w >>= col;
+      // most blocks are fully visible (only e.g. the diagonal ones carry a causal pattern): skip the bit tests there
+      const uint64_t mine = (w >> col) & ((1ull << EPL) - 1ull);
+      if (mine != ((1ull << EPL) - 1ull)) {
 #pragma unroll
-      for (int i = 0; i < EPL; ++i) if (!((w >> i) & 1ull)) v[i] = -FLT_MAX;
+        for (int i = 0; i < EPL; ++i) if (!((mine >> i) & 1ull)) v[i] = -FLT_MAX;
+      }
     }
   };
 
   // Pass A (one read of the row): online max / sum -- (m, s) with s = sum exp(v - m), rescaled whenever m grows.
   constexpr float LOG2E = 1.4426950408889634f;
+  // exp2 is the other bound of this kernel (MUFU: 16/clk/SM, i.e. ~0.1 ms for cfg 3 if every element needed two):
+  // kept entries are exponentiated ONCE, against the running max at that time (mref[e]), and rescaled by one
+  // scalar exp2 per entry at the end.
   float keep[KEEP][EPL];
+  float mref[KEEP];
   float m = -FLT_MAX, s = 0.f;
-  auto absorb = [&](const float (&v)[EPL]) {
+  auto absorb = [&](float (&v)[EPL]) -> float {
     float mv = v[0];
 #pragma unroll
     for (int i = 1; i < EPL; ++i) mv = fmaxf(mv, v[i]);
     const float mn = fmaxf(m, mv);
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) acc += exp2f((v[i] - mn) * LOG2E);
+    for (int i = 0; i < EPL; ++i) { v[i] = exp2f((v[i] - mn) * LOG2E); acc += v[i]; }
     s = s * exp2f((m - mn) * LOG2E) + acc;
     m = mn;
+    return mn;
   };
 #pragma unroll
   for (int e = 0; e < KEEP; ++e) {
-    if (e < count) { load_entry(e, keep[e]); absorb(keep[e]); }
+    mref[e] = 0.f;
+    if (e < count) { load_entry(e, keep[e]); mref[e] = absorb(keep[e]); }
   }
 #pragma unroll 4
   for (int e = KEEP; e < count; ++e) {
@@ -197,8 +206,9 @@ bst_softmax_kernel(const SoftmaxParams p) {
   for (int e = 0; e < KEEP; ++e) {
     if (e < count) {
       int blk, kb; entry(e, blk, kb);
+      const float sc = exp2f((mref[e] - m) * LOG2E) * inv;
 #pragma unroll
-      for (int i = 0; i < EPL; ++i) keep[e][i] = exp2f((keep[e][i] - m) * LOG2E) * inv;
+      for (int i = 0; i < EPL; ++i) keep[e][i] *= sc;
       store_vec<TY, EPL>(y + (zoff + blk) * (BS * BS), keep[e]);
     }
   }
