@@ -73,6 +73,11 @@ def device_error():
     return load().bsmm_device_error()
 
 
+def device_error_text():
+    """Message recorded by the last failing call (e.g. the CUDA fault string behind device_error() == -1)."""
+    return load().bsmm_last_error().decode("utf-8", "replace")
+
+
 def last_kernel():
     return load().bsmm_last_kernel().decode()
 

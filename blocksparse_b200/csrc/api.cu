@@ -24,7 +24,8 @@ int bsmm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int bsmm_device_error(void) {
   int v = 0, zero = 0;
-  if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaGetLastError(); fail((int)e, "device fault: %s", cudaGetErrorString(e)); return -1; }
   if (cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int)) != cudaSuccess) return -1;
   if (v != 0) cudaMemcpyToSymbol(g_tc_error, &zero, sizeof(int));
   return v;

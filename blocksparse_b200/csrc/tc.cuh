@@ -73,6 +73,10 @@ template <> struct XpropCfg<32, 2, 1> {
   static constexpr int XS = 6, WPS = 2, STG = 4, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
 };
+template <> struct XpropCfg<32, 2, 3> {
+  static constexpr int XS = 6, WPS = 4, STG = 2, TCOLS = 256;
+  static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
+};
 template <> struct XpropCfg<32, 1> {
   static constexpr int XS = 6, WPS = 8, STG = 8, TCOLS = 512;  // group stages, W slots per stage, staging buffers, TMEM columns
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;     // 64-byte rows
@@ -81,11 +85,11 @@ template <> struct XpropCfg<32, 1> {
 // (profiles/r1_xprop_tuning.txt): XS=6/WPS=4/STG=0 is ~7 % SLOWER at 25 % density and 23 % slower at 100 % than
 // XS=3/WPS=8/STG=4, so the staged TMA-store epilogue stays.
 template <> struct XpropCfg<32, 2> {
-  static constexpr int XS = 3, WPS = 8, STG = 4, TCOLS = 256;
+  static constexpr int XS = 4, WPS = 8, STG = 2, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
 };
 template <> struct XpropCfg<64, 1> {
-  static constexpr int XS = 3, WPS = 4, STG = 4, TCOLS = 512;
+  static constexpr int XS = 4, WPS = 4, STG = 2, TCOLS = 512;
   static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;   // 128-byte rows
 };
 template <> struct XpropCfg<64, 2> {
@@ -93,7 +97,8 @@ template <> struct XpropCfg<64, 2> {
   static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;
 };
 constexpr int XPROP_PRODUCERS = 2;
-constexpr int XPROP_THREADS = (XPROP_PRODUCERS + 1 + 4) * 32;
+constexpr int XPROP_ISSUERS = 2;                   // MMA-issuing warps, alternating groups like the producers
+constexpr int XPROP_THREADS = (XPROP_PRODUCERS + XPROP_ISSUERS + 4) * 32;
 
 // sticky device-side error word: a kernel whose bounded wait timed out stores a non-zero code here
 __device__ int g_tc_error = 0;
@@ -117,6 +122,10 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   using Cfg = XpropCfg<BS, OCC, VAR>;
   constexpr int XS = Cfg::XS, WPS = Cfg::WPS, STG = Cfg::STG;
   constexpr int KS = BS / 16;                     // K=16 slices per block
+  // Two independent in-order pipelines (producer warp p -> issuer warp p) share the ring: pipeline p owns the
+  // stages with index % 2 == p, so every mbarrier has one waiter that walks its phases in order.
+  static_assert(XPROP_PRODUCERS == XPROP_ISSUERS && XS % XPROP_PRODUCERS == 0, "stages are split evenly between the pipelines");
+  constexpr uint32_t HS = XS / XPROP_PRODUCERS;   // stages per pipeline
   constexpr uint32_t XBYTES = 128 * BS * 2, WBYTES = BS * BS * 2;
   constexpr uint32_t STAGE_BYTES = XBYTES + WPS * WBYTES;
   constexpr uint32_t ROW = BS * 2;                // bytes per smem row (== swizzle span)
@@ -124,7 +133,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sStage = smem;                         // XS x (activation tile | WPS W blocks)
   uint8_t* sO = smem + XS * STAGE_BYTES;          // STG x XBYTES staging for the output tile
-  __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty;
+  __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty, turn[XPROP_ISSUERS];
   __shared__ __align__(16) int4 cmd[XS][8];       // per run: (B descriptor low word for K slice 0, D tmem address, idesc, accumulate)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
@@ -137,8 +146,9 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   if (tid == 0) {
     abort_s = 0;
     for (int i = 0; i < XS; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    ptx::mbar_init(&acc_full, 1);
+    ptx::mbar_init(&acc_full, XPROP_ISSUERS);
     ptx::mbar_init(&acc_empty, 1);
+    for (int i = 0; i < XPROP_ISSUERS; ++i) ptx::mbar_init(&turn[i], 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&maps.x); ptx::prefetch_tensormap(&maps.w); ptx::prefetch_tensormap(&maps.y);
   }
@@ -170,12 +180,14 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         const int cur = rec;
         const int gn = g + XPROP_PRODUCERS;
         if (gn < n_groups) rec = grec[gn * 32 + lane];          // prefetch the next record
+        // pipeline `warp` (this producer + issuer warp `warp`) owns the stages st % 2 == warp and runs them in order
         const uint32_t gc = gbase + g;
-        const uint32_t st = gc % XS;
+        const uint32_t pj = gc / XPROP_PRODUCERS;                  // running group count of this pipeline
+        const uint32_t st = (uint32_t)warp + XPROP_PRODUCERS * (pj % HS);
         const int in_blk = __shfl_sync(0xffffffffu, cur, 0);
         const int counts = __shfl_sync(0xffffffffu, cur, 1);
         const int n_w = counts & 0xff, n_runs = counts >> 8;
-        if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(empty0 + st * 8, ((gc / XS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(empty0 + st * 8, ((pj / HS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
         // lanes 12..19 hold int0 of run (lane-12); int1 sits 8 lanes up.  They write the ready-to-issue
         // command so the issuing thread only moves registers.
         const uint32_t r1 = (uint32_t)__shfl_down_sync(0xffffffffu, cur, 8);
@@ -203,10 +215,16 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       }
       gbase += n_groups;
     }
-  } else if (warp == XPROP_PRODUCERS) {
-    // ================================ MMA issuer ================================
+  } else if (warp < XPROP_PRODUCERS + XPROP_ISSUERS) {
+    // ================================ MMA issuers ================================
+    // Two warps, each with one elected issuing thread, alternate groups (running group index gc % 2): a group
+    // costs its issuing warp ~150 instructions (barrier wait, command fetch, descriptor moves to uniform
+    // registers) for ~3 tcgen05.mma, and that instruction stream -- not the tensor pipe -- bounded the
+    // single-issuer kernel (profiles/r1_xprop_tuning.txt).  Accumulators start from zero (the epilogue clears
+    // them), so every MMA accumulates and the order in which the two warps' MMAs reach the pipe is irrelevant.
     // fprop: B = W[c][k] read as K x N with N contiguous (MN-major): K=16 slice = 16 rows, blocks LBO apart.
     // bprop: B = W[c][k] read as N x K with K contiguous (K-major):  K=16 slice = 32 bytes along the row.
+    const uint32_t iw = (uint32_t)(warp - XPROP_PRODUCERS);
     const uint32_t b_kstep16 = (p.bprop ? 32u : 16u * ROW) >> 4;
     // axis 1: A = X[n][c] tile, K-major, rows of bs*2 bytes, K=16 slice = +32 B.
     // axis 0: A = X[c][n] tile, MN-major SW128: two [bs x 64] boxes (LBO = box), 8-row groups 1 KB apart, K=16 slice = 16 rows.
@@ -216,16 +234,26 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     const uint32_t b_desc_hi = (uint32_t)(ptx::make_smem_desc(0, 16, Cfg::SBO, Cfg::SWZ) >> 32);
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
                    cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0]));
-    uint32_t st = 0, ph = 0, tile_it = 0;          // pipeline stage and its phase bit, advanced incrementally
+    uint32_t tile_it = 0, gbase = 0;
     const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
     bool alive = true;
     for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x, ++tile_it) {
       const int kt = t % p.n_ktiles;
       const int n_groups = sched[4 + 4 * kt + 1];
-      if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, (tile_it & 1) ^ 1, abort_flag))) { g_tc_error = 3; break; }
+      if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, tile_it & 1, abort_flag))) { g_tc_error = 3; break; }
       ptx::tc_fence_after();
-      for (int g = 0; g < n_groups; ++g) {
+      int g = (int)((XPROP_ISSUERS + iw - (gbase % XPROP_ISSUERS)) % XPROP_ISSUERS);   // first group of this tile owned by this warp
+      uint32_t pj = (gbase + g) / XPROP_ISSUERS;                   // running group count of this pipeline
+      uint32_t js = pj % HS, ph = (pj / HS) & 1;                   // slot within this pipeline's stages, phase bit
+      for (; g < n_groups; g += XPROP_ISSUERS) {
+        const uint32_t st = iw + XPROP_ISSUERS * js;
         if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(full0 + st * 8, ph, abort_flag))) { g_tc_error = 4; alive = false; break; }
+        // The two warps take turns in group order (group gc issues after group gc-1), so every accumulator sees
+        // its MMAs in schedule order and results are bit-identical run to run.  Only the short issue section is
+        // serialised; barrier waits, command fetches and descriptor set-up of the two warps still overlap.
+        const bool my_turn = (iw == 0) ? (pj == 0 || ptx::mbar_wait(&turn[0], (pj - 1) & 1, abort_flag))
+                                       : ptx::mbar_wait(&turn[1], pj & 1, abort_flag);
+        if (!__all_sync(0xffffffffu, my_turn)) { g_tc_error = 5; alive = false; break; }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t a_lo = a_lo0 + st * (STAGE_BYTES >> 4);
@@ -250,25 +278,35 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             for (int r = 0; r < 8; ++r) {
               if (r >= n_runs) break;              // a real (uniform) branch: skipped runs cost nothing
               const uint64_t bdesc = ((uint64_t)b_desc_hi << 32) | (uint32_t)((uint32_t)c[r].x + ks * b_kstep16);
-              const uint32_t acc = (ks > 0) ? 1u : ((uint32_t)c[r].w & 1u);
-              if (r == 0) ptx::mma_ss_a_fill((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
-              else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, acc);
+              if (r == 0) ptx::mma_ss_a_fill((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, 1u);
+              else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, 1u);
             }
           }
           ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&turn[iw ^ 1]);     // hand the turn to the other issuer
         }
         __syncwarp();
-        if (++st == XS) { st = 0; ph ^= 1; }
+        ++pj;
+        if (++js == HS) { js = 0; ph ^= 1; }
       }
-      if (ptx::elect_one()) ptx::tc_commit(&acc_full);
+      if (ptx::elect_one()) ptx::tc_commit(&acc_full);   // arrives when this warp's MMAs of the tile have retired
       __syncwarp();
+      gbase += (uint32_t)n_groups;
     }
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;                  // row of the 128-row tile
-    const int etid = (warp - XPROP_PRODUCERS - 1) * 32 + lane;
+    const int etid = (warp - XPROP_PRODUCERS - XPROP_ISSUERS) * 32 + lane;
     uint32_t tile_it = 0;
+    // accumulators start from zero: clear this warp's lanes once, then after every read-out
+#pragma unroll
+    for (int c = 0; c < Cfg::TCOLS; c += 32) ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (etid == 0) ptx::mbar_arrive(&acc_empty);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
       const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
       const int32_t* th = sched + 4 + 4 * kt;
@@ -291,6 +329,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             if ((mask >> slot) & 1u) {
               ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
               ptx::tmem_ld_wait();
+              ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -306,6 +345,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             }
           }
         }
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (etid == 0) ptx::mbar_arrive(&acc_empty);
@@ -320,6 +360,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             if ((mask >> slot) & 1u) {
               ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
               ptx::tmem_ld_wait();
+              ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -339,6 +380,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             }
           }
         }
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (etid == 0) ptx::mbar_arrive(&acc_empty);
@@ -356,6 +398,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             if ((mask >> slot) & 1u) {
               ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
               ptx::tmem_ld_wait();
+              ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;    // output block with an empty LUT row
@@ -375,6 +418,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
             }
           }
         }
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -460,6 +504,10 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
       sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
     return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
                 p.n_ktiles, tile_blocks, n_out);
+  if (occ == 2 && bsize == 32 && w_per_group == 4) {
+    return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 3>(p, maps, dev.sm_count, s)
+                              : launch_tc_xprop<32, false, 2, 3>(p, maps, dev.sm_count, s);
+  }
   if (w_per_group != 0 && !(bsize == 32 && occ == 2 && w_per_group == 2) &&
       w_per_group != (bsize == 32 ? 8 : (occ == 2 ? 2 : 4)))
     return fail(BSMM_E_ARG, "bsmm_xprop: schedule built with %d W blocks per group, no kernel variant matches", w_per_group);

@@ -19,6 +19,7 @@ import os
 # Output blocks per xprop tile.  Full width (512 TMEM columns: 16 / 8 blocks) runs one CTA per SM; half width
 # (8 / 4 blocks) runs two CTAs -- two MMA-issuing threads -- per SM (csrc/tc.cuh XpropCfg<BS, OCC>).
 _HALF = os.environ.get("BSMM_XPROP_OCC", "2") == "2"
+_WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))
 _TILE_BLOCKS = {32: 8, 64: 4} if _HALF else {32: 16, 64: 8}
 # W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
 _W_PER_GROUP = ({32: 8, 64: 2} if _HALF else {32: 8, 64: 4})
@@ -160,7 +161,12 @@ class BlocksparseMatMul(object):
             sparse = _HALF and self.bsize == 32 and self.blocks * tb <= 1.0 * self.CB * self.KB
             if sparse:
                 wpg = 2
-            key = (bool(bprop), n_kt)
+            elif _HALF and self.bsize == 32 and _WPG_OVERRIDE:
+                wpg, sparse = _WPG_OVERRIDE, True
+            elif _HALF and self.bsize == 32 and self.blocks * tb <= 3.0 * self.CB * self.KB:
+                # 1..3 W blocks per group on average (density <= 37.5 %): 4 W slots per stage, 6 stages in flight
+                wpg, sparse = 4, True
+            key = (bool(bprop), n_kt, wpg)
             if key not in d["xprop_sched"]:
                 arr, off = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt)
                 d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off)

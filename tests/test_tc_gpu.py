@@ -55,7 +55,7 @@ def test_tc_xprop_matches_oracle(case, dtype, axis):
     for name, got_fn, ref in [("fprop", lambda: bsmm.fprop(X.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_TC), orc.fprop_dense(Xn, Wn)),
                               ("bprop", lambda: bsmm.bprop(E.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_TC), orc.bprop_dense(En, Wn))]:
         got = got_fn()
-        assert _lib.device_error() == 0, "a tcgen05 kernel hit its bounded-wait timeout"
+        assert _lib.device_error() == 0, "a tcgen05 kernel hit its bounded-wait timeout or faulted: " + _lib.device_error_text()
         assert _lib.last_kernel().startswith("tcgen05_xprop"), _lib.last_kernel()
         mx, l2 = ref_errors(got.float().cpu().numpy(), ref)
         assert l2 <= (4e-3 if dtype == torch.bfloat16 else 1e-3), "%s l2 %.3e max %.3e" % (name, l2, mx)
@@ -113,7 +113,7 @@ def test_tc_updat_matches_oracle(case, dtype, axis):
         ref += orc.updat_dense(X.float().numpy(), E.float().numpy())
     # fp32 output: only the 16-bit INPUT rounding separates us from the oracle (which sees the same rounded inputs)
     dw32 = bsmm.updat(xs, es, dw_dtype=torch.float32, flags=_lib.FLAG_FORCE_TC)
-    assert _lib.device_error() == 0, "a tcgen05 kernel hit its bounded-wait timeout"
+    assert _lib.device_error() == 0, "a tcgen05 kernel hit its bounded-wait timeout or faulted: " + _lib.device_error_text()
     assert _lib.last_kernel().startswith("tcgen05_updat"), _lib.last_kernel()
     mx, l2 = ref_errors(dw32.cpu().numpy(), ref)
     assert l2 <= 1e-5 and mx <= 1e-4, "fp32-out updat l2 %.3e max %.3e" % (l2, mx)
