@@ -70,35 +70,35 @@ inline int make_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t in
 // 8, which doubles the number of stages in flight -- at 5-10 % density the kernel is bound by the TMA round trip.
 template <int BS, int OCC, int VAR = 0> struct XpropCfg;
 template <> struct XpropCfg<32, 2, 1> {
-  static constexpr int XS = 6, WPS = 2, STG = 4, TCOLS = 256;
+  static constexpr int XS = 6, WPS = 2, STG = 4, NP = 2, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
 };
 template <> struct XpropCfg<32, 2, 3> {
-  static constexpr int XS = 6, WPS = 4, STG = 2, TCOLS = 256;
+  static constexpr int XS = 6, WPS = 4, STG = 2, NP = 2, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
 };
 template <> struct XpropCfg<32, 1> {
-  static constexpr int XS = 6, WPS = 8, STG = 8, TCOLS = 512;  // group stages, W slots per stage, staging buffers, TMEM columns
+  static constexpr int XS = 6, WPS = 8, STG = 8, NP = 3, TCOLS = 512;  // group stages, W slots per stage, staging buffers, TMEM columns
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;     // 64-byte rows
 };
 // STG == 0 selects a direct epilogue (rows stored straight from registers, no staging).  Measured on B200
 // (profiles/r1_xprop_tuning.txt): XS=6/WPS=4/STG=0 is ~7 % SLOWER at 25 % density and 23 % slower at 100 % than
 // XS=3/WPS=8/STG=4, so the staged TMA-store epilogue stays.
 template <> struct XpropCfg<32, 2> {
-  static constexpr int XS = 4, WPS = 8, STG = 2, TCOLS = 256;
+  static constexpr int XS = 4, WPS = 8, STG = 2, NP = 4, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
 };
 template <> struct XpropCfg<64, 1> {
-  static constexpr int XS = 4, WPS = 4, STG = 2, TCOLS = 512;
+  static constexpr int XS = 4, WPS = 4, STG = 2, NP = 2, TCOLS = 512;
   static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;   // 128-byte rows
 };
 template <> struct XpropCfg<64, 2> {
-  static constexpr int XS = 2, WPS = 2, STG = 2, TCOLS = 256;
+  static constexpr int XS = 2, WPS = 2, STG = 2, NP = 2, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;
 };
-constexpr int XPROP_PRODUCERS = 2;
-constexpr int XPROP_ISSUERS = 2;                   // MMA-issuing warps, alternating groups like the producers
-constexpr int XPROP_THREADS = (XPROP_PRODUCERS + XPROP_ISSUERS + 4) * 32;
+// Cfg::NP = number of pipelines: NP producer warps + NP MMA-issuing warps (pipeline p = producer p -> issuer p,
+// groups dealt round-robin) + 4 epilogue warps.
+template <class Cfg> constexpr int xprop_threads() { return (2 * Cfg::NP + 4) * 32; }
 
 // sticky device-side error word: a kernel whose bounded wait timed out stores a non-zero code here
 __device__ int g_tc_error = 0;
@@ -117,15 +117,16 @@ struct XpropTcParams {
 struct XpropTmaps { CUtensorMap x, w, y; };
 
 template <int BS, bool BF16, int OCC, int VAR = 0>
-__global__ void __launch_bounds__(XPROP_THREADS, OCC)
+__global__ void __launch_bounds__((xprop_threads<XpropCfg<BS, OCC, VAR>>()), OCC)
 tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) {
   using Cfg = XpropCfg<BS, OCC, VAR>;
   constexpr int XS = Cfg::XS, WPS = Cfg::WPS, STG = Cfg::STG;
   constexpr int KS = BS / 16;                     // K=16 slices per block
   // Two independent in-order pipelines (producer warp p -> issuer warp p) share the ring: pipeline p owns the
   // stages with index % 2 == p, so every mbarrier has one waiter that walks its phases in order.
-  static_assert(XPROP_PRODUCERS == XPROP_ISSUERS && XS % XPROP_PRODUCERS == 0, "stages are split evenly between the pipelines");
-  constexpr uint32_t HS = XS / XPROP_PRODUCERS;   // stages per pipeline
+  constexpr int NP = Cfg::NP;
+  static_assert(XS % NP == 0, "stages are split evenly between the pipelines");
+  constexpr uint32_t HS = XS / NP;   // stages per pipeline
   constexpr uint32_t XBYTES = 128 * BS * 2, WBYTES = BS * BS * 2;
   constexpr uint32_t STAGE_BYTES = XBYTES + WPS * WBYTES;
   constexpr uint32_t ROW = BS * 2;                // bytes per smem row (== swizzle span)
@@ -133,7 +134,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sStage = smem;                         // XS x (activation tile | WPS W blocks)
   uint8_t* sO = smem + XS * STAGE_BYTES;          // STG x XBYTES staging for the output tile
-  __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty, turn[XPROP_ISSUERS];
+  __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty, turn[NP];
   __shared__ __align__(16) int4 cmd[XS][8];       // per run: (B descriptor low word for K slice 0, D tmem address, idesc, accumulate)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
@@ -146,22 +147,22 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   if (tid == 0) {
     abort_s = 0;
     for (int i = 0; i < XS; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    ptx::mbar_init(&acc_full, XPROP_ISSUERS);
+    ptx::mbar_init(&acc_full, NP);
     ptx::mbar_init(&acc_empty, 1);
-    for (int i = 0; i < XPROP_ISSUERS; ++i) ptx::mbar_init(&turn[i], 1);
+    for (int i = 0; i < NP; ++i) ptx::mbar_init(&turn[i], 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&maps.x); ptx::prefetch_tensormap(&maps.w); ptx::prefetch_tensormap(&maps.y);
   }
-  if (warp == XPROP_PRODUCERS) { ptx::tmem_alloc(&tmem_base_s, Cfg::TCOLS); ptx::tmem_relinquish(); }
+  if (warp == NP) { ptx::tmem_alloc(&tmem_base_s, Cfg::TCOLS); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < XPROP_PRODUCERS) {
+  if (warp < NP) {
     // ================================ TMA producers ================================
     // Producer `warp` owns the groups whose running index gc (over all tiles of this CTA) has
-    // gc % XPROP_PRODUCERS == warp; lane i holds int i of the group record.
+    // gc % NP == warp; lane i holds int i of the group record.
     uint32_t gbase = 0;                   // groups of earlier tiles
     bool alive = true;
     const uint32_t p_idesc0 = ptx::make_idesc_f16(BF16, p.axis0 != 0, !p.bprop, 128, 0);
@@ -174,16 +175,16 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       const int first_group = th[0], n_groups = th[1];
       const int32_t* grec = sched + p.groups_off + (size_t)first_group * 32;
       // first group of this tile owned by this warp
-      int g = (int)((XPROP_PRODUCERS + warp - (gbase % XPROP_PRODUCERS)) % XPROP_PRODUCERS);
+      int g = (int)((NP + warp - (gbase % NP)) % NP);
       int rec = (g < n_groups) ? grec[g * 32 + lane] : 0;
-      for (; g < n_groups; g += XPROP_PRODUCERS) {
+      for (; g < n_groups; g += NP) {
         const int cur = rec;
-        const int gn = g + XPROP_PRODUCERS;
+        const int gn = g + NP;
         if (gn < n_groups) rec = grec[gn * 32 + lane];          // prefetch the next record
         // pipeline `warp` (this producer + issuer warp `warp`) owns the stages st % 2 == warp and runs them in order
         const uint32_t gc = gbase + g;
-        const uint32_t pj = gc / XPROP_PRODUCERS;                  // running group count of this pipeline
-        const uint32_t st = (uint32_t)warp + XPROP_PRODUCERS * (pj % HS);
+        const uint32_t pj = gc / NP;                  // running group count of this pipeline
+        const uint32_t st = (uint32_t)warp + NP * (pj % HS);
         const int in_blk = __shfl_sync(0xffffffffu, cur, 0);
         const int counts = __shfl_sync(0xffffffffu, cur, 1);
         const int n_w = counts & 0xff, n_runs = counts >> 8;
@@ -215,7 +216,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       }
       gbase += n_groups;
     }
-  } else if (warp < XPROP_PRODUCERS + XPROP_ISSUERS) {
+  } else if (warp < 2 * NP) {
     // ================================ MMA issuers ================================
     // Two warps, each with one elected issuing thread, alternate groups (running group index gc % 2): a group
     // costs its issuing warp ~150 instructions (barrier wait, command fetch, descriptor moves to uniform
@@ -224,7 +225,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     // them), so every MMA accumulates and the order in which the two warps' MMAs reach the pipe is irrelevant.
     // fprop: B = W[c][k] read as K x N with N contiguous (MN-major): K=16 slice = 16 rows, blocks LBO apart.
     // bprop: B = W[c][k] read as N x K with K contiguous (K-major):  K=16 slice = 32 bytes along the row.
-    const uint32_t iw = (uint32_t)(warp - XPROP_PRODUCERS);
+    const uint32_t iw = (uint32_t)(warp - NP);
     const uint32_t b_kstep16 = (p.bprop ? 32u : 16u * ROW) >> 4;
     // axis 1: A = X[n][c] tile, K-major, rows of bs*2 bytes, K=16 slice = +32 B.
     // axis 0: A = X[c][n] tile, MN-major SW128: two [bs x 64] boxes (LBO = box), 8-row groups 1 KB apart, K=16 slice = 16 rows.
@@ -242,17 +243,17 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
       const int n_groups = sched[4 + 4 * kt + 1];
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, tile_it & 1, abort_flag))) { g_tc_error = 3; break; }
       ptx::tc_fence_after();
-      int g = (int)((XPROP_ISSUERS + iw - (gbase % XPROP_ISSUERS)) % XPROP_ISSUERS);   // first group of this tile owned by this warp
-      uint32_t pj = (gbase + g) / XPROP_ISSUERS;                   // running group count of this pipeline
+      int g = (int)((NP + iw - (gbase % NP)) % NP);   // first group of this tile owned by this warp
+      uint32_t pj = (gbase + g) / NP;                   // running group count of this pipeline
       uint32_t js = pj % HS, ph = (pj / HS) & 1;                   // slot within this pipeline's stages, phase bit
-      for (; g < n_groups; g += XPROP_ISSUERS) {
-        const uint32_t st = iw + XPROP_ISSUERS * js;
+      for (; g < n_groups; g += NP) {
+        const uint32_t st = iw + NP * js;
         if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(full0 + st * 8, ph, abort_flag))) { g_tc_error = 4; alive = false; break; }
         // The two warps take turns in group order (group gc issues after group gc-1), so every accumulator sees
         // its MMAs in schedule order and results are bit-identical run to run.  Only the short issue section is
         // serialised; barrier waits, command fetches and descriptor set-up of the two warps still overlap.
         const bool my_turn = (iw == 0) ? (pj == 0 || ptx::mbar_wait(&turn[0], (pj - 1) & 1, abort_flag))
-                                       : ptx::mbar_wait(&turn[1], pj & 1, abort_flag);
+                                       : ptx::mbar_wait(&turn[iw], pj & 1, abort_flag);
         if (!__all_sync(0xffffffffu, my_turn)) { g_tc_error = 5; alive = false; break; }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -284,7 +285,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
           }
           ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&turn[iw ^ 1]);     // hand the turn to the other issuer
+          ptx::mbar_arrive(&turn[iw + 1 == NP ? 0 : iw + 1]);     // hand the turn to the next issuer
         }
         __syncwarp();
         ++pj;
@@ -298,7 +299,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     // ================================ epilogue ================================
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;                  // row of the 128-row tile
-    const int etid = (warp - XPROP_PRODUCERS - XPROP_ISSUERS) * 32 + lane;
+    const int etid = (warp - 2 * NP) * 32 + lane;
     uint32_t tile_it = 0;
     // accumulators start from zero: clear this warp's lanes once, then after every read-out
 #pragma unroll
@@ -435,7 +436,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == XPROP_PRODUCERS) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
+  if (warp == NP) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
 template <int BS, int OCC, int VAR = 0>
@@ -456,7 +457,7 @@ int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count
   }
   const int total = p.n_ktiles * p.n_ntiles;
   const int grid = total < sm_count * OCC ? total : sm_count * OCC;
-  kern<<<grid, XPROP_THREADS, smem, s>>>(p, maps);
+  kern<<<grid, xprop_threads<XpropCfg<BS, OCC, VAR>>(), smem, s>>>(p, maps);
   return check_launch(BS == 32 ? "tcgen05_xprop_bs32" : "tcgen05_xprop_bs64");
 }
 

@@ -16,13 +16,15 @@ from .lut import MatmulLuts, pick_tile_count
 # tcgen05 tile width (output blocks whose accumulators share one CTA's tensor memory)
 import os
 
-# Output blocks per xprop tile.  Full width (512 TMEM columns: 16 / 8 blocks) runs one CTA per SM; half width
-# (8 / 4 blocks) runs two CTAs -- two MMA-issuing threads -- per SM (csrc/tc.cuh XpropCfg<BS, OCC>).
-_HALF = os.environ.get("BSMM_XPROP_OCC", "2") == "2"
+# Output blocks per xprop tile and CTAs per SM (csrc/tc.cuh XpropCfg<BS, OCC>), picked from B200 timings
+# (profiles/r1_xprop_tuning.txt): 32x32 blocks run best as half-width tiles (8 blocks = 256 TMEM columns) with two
+# CTAs per SM, 64x64 blocks as full-width tiles (8 blocks = 512 columns) with one.  BSMM_XPROP_OCC=1|2 forces one.
+_OCC_ENV = os.environ.get("BSMM_XPROP_OCC", "")
+_OCC = {32: 2, 64: 1} if _OCC_ENV not in ("1", "2") else {32: int(_OCC_ENV), 64: int(_OCC_ENV)}
 _WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))
-_TILE_BLOCKS = {32: 8, 64: 4} if _HALF else {32: 16, 64: 8}
+_TILE_BLOCKS = {bs: (256 if occ == 2 else 512) // bs for bs, occ in _OCC.items()}
 # W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
-_W_PER_GROUP = ({32: 8, 64: 2} if _HALF else {32: 8, 64: 4})
+_W_PER_GROUP = {32: 8, 64: 2 if _OCC[64] == 2 else 4}
 
 
 def _as_2d(t, axis, feat):
@@ -122,7 +124,7 @@ class BlocksparseMatMul(object):
             tb = _TILE_BLOCKS.get(self.bsize)
             if tb:
                 d["xprop_sched"] = {}          # (bprop, n_tiles) -> (tensor, n_tiles, groups_off), built on demand
-                d["cta_slots"] = torch.cuda.get_device_properties(device).multi_processor_count * (2 if _HALF else 1)
+                d["cta_slots"] = torch.cuda.get_device_properties(device).multi_processor_count * _OCC[self.bsize]
                 us, uoff = self._luts.updat_schedule(self.bsize)
                 d["updat_sched"] = torch.as_tensor(us, device=device)
                 d["updat_tiles"], d["updat_kt"] = int(us[0]), int(us[2])
@@ -158,12 +160,12 @@ class BlocksparseMatMul(object):
             n_kt = pick_tile_count(n_out, -(-N // 128), d["cta_slots"], tb)
             # sparse layouts (about one W block per group) use 2 W slots per stage => twice the stages in flight
             wpg = _W_PER_GROUP[self.bsize]
-            sparse = _HALF and self.bsize == 32 and self.blocks * tb <= 1.0 * self.CB * self.KB
+            sparse = _OCC[32] == 2 and self.bsize == 32 and self.blocks * tb <= 1.0 * self.CB * self.KB
             if sparse:
                 wpg = 2
-            elif _HALF and self.bsize == 32 and _WPG_OVERRIDE:
+            elif _OCC[32] == 2 and self.bsize == 32 and _WPG_OVERRIDE:
                 wpg, sparse = _WPG_OVERRIDE, True
-            elif _HALF and self.bsize == 32 and self.blocks * tb <= 3.0 * self.CB * self.KB:
+            elif _OCC[32] == 2 and self.bsize == 32 and self.blocks * tb <= 3.0 * self.CB * self.KB:
                 # 1..3 W blocks per group on average (density <= 37.5 %): 4 W slots per stage, 6 stages in flight
                 wpg, sparse = 4, True
             key = (bool(bprop), n_kt, wpg)
