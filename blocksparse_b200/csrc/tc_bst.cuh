@@ -21,6 +21,7 @@ namespace bsmm {
 
 constexpr int BST_THREADS = 6 * 32;      // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 constexpr int BST_STAGES = 4;
+constexpr int BST_NT_STAGES = 3;
 constexpr uint32_t BST_TILE = 64 * 64 * 2;   // one 64 x 64 16-bit tile with 128-byte rows (SW128)
 
 // ------------------------------------------------------------------------------------------------
@@ -30,16 +31,18 @@ struct BstNtParams {
   int batch, heads, blocks, head_state;
   int ctx_rows_a, ctx_rows_b;   // rows per batch element of a / b
   void* c;
+  int tma_store;            // 16-bit outputs: stage the 8 KB block in shared memory and store it with one TMA op
 };
-struct BstNtTmaps { CUtensorMap a, b; };
+struct BstNtTmaps { CUtensorMap a, b, c; };   // c: the sparse output as [batch*heads*blocks*64][64] (16-bit outputs only)
 
 template <bool BF16, typename TC>
-__global__ void __launch_bounds__(BST_THREADS, 1)
+__global__ void __launch_bounds__(BST_THREADS, 2)
 tc_bst_nt_kernel(const BstNtParams p, const __grid_constant__ BstNtTmaps maps) {
-  constexpr int ST = BST_STAGES;
+  constexpr int ST = BST_NT_STAGES;                        // 72 KB of stages + 32 KB of output staging: two CTAs per SM
   constexpr uint32_t STAGE_BYTES = 3 * BST_TILE;          // two query tiles + one key tile
   constexpr int NBUF = 4;                                  // accumulator buffers of 64 columns
   extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sOut = smem + ST * STAGE_BYTES;                 // 2 x (two 8 KB blocks) of output staging
   __shared__ uint64_t full[ST], empty[ST], acc_full[NBUF], acc_empty[NBUF];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
@@ -128,6 +131,47 @@ tc_bst_nt_kernel(const BstNtParams p, const __grid_constant__ BstNtTmaps maps) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*abort_flag) { g_tc_error = 26; break; }
       ptx::tc_fence_after();
+      if constexpr (sizeof(TC) == 2) {
+        if (p.tma_store) {
+          // A thread owns one 128-byte row of a block; writing rows straight to global memory costs one 16-byte
+          // request per lane (profiles: L1->L2 request port 56 % busy, HBM 41 %).  Stage the block swizzled (the
+          // layout the SW128 tensor map expects) and let one TMA store write the contiguous 8 KB.
+          uint8_t* sbuf = sOut + (n & 1u) * (2 * BST_TILE);
+          if (warp == 2 && lane == 0) ptx::tma_store_wait_read<1>();      // the store that last read this buffer is done
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (half < nv) {
+            uint8_t* dst = sbuf + half * BST_TILE + row * 128;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[32];
+              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + buf * 64 + hh * 32, v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = __uint_as_float(v[8 * i + 2 * e]), bq = __uint_as_float(v[8 * i + 2 * e + 1]);
+                  typename Pair<TC>::type q; q.x = from_f32<TC>(a); q.y = from_f32<TC>(bq);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&q);
+                }
+                const uint32_t chunk = (uint32_t)(hh * 4 + i);
+                *reinterpret_cast<uint4*>(dst + ((chunk ^ ((uint32_t)row & 7u)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            ptx::mbar_arrive(&acc_empty[buf]);
+            for (int hb = 0; hb < nv; ++hb)
+              ptx::tma_store_2d(&maps.c, sbuf + hb * BST_TILE, 0, (int)(((long long)bh * p.blocks + rec[2 + 2 * hb]) * 64));
+            ptx::tma_store_commit();
+          }
+          continue;
+        }
+      }
       if (half < nv) {
         TC* out = cbase + (((size_t)bh * p.blocks + blk) * 64 + row) * 64;
 #pragma unroll
@@ -159,6 +203,7 @@ tc_bst_nt_kernel(const BstNtParams p, const __grid_constant__ BstNtTmaps maps) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 2 && lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
+    if (warp == 2 && lane == 0) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -179,11 +224,13 @@ struct BstXnParams {
 struct BstXnTmaps { CUtensorMap a, b; };
 
 template <bool BF16>
-__global__ void __launch_bounds__(BST_THREADS, 1)
+__global__ void __launch_bounds__(BST_THREADS, 2)
 tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
   constexpr int ST = BST_STAGES;
-  // stage: A region 2 tiles (64 valid rows + 64 stale rows read by the M=128 MMA) + B up to 2 tiles (head_state <= 128)
-  constexpr uint32_t STAGE_BYTES = 4 * BST_TILE;
+  // stage: A tile (64 valid rows) + B up to 2 tiles (head_state <= 128).  The M=128 MMA also reads 64 rows past the
+  // A tile -- that is the first B tile; those accumulator lanes (64..127) are never read back.  96 KB of stages and
+  // 256 TMEM columns per CTA => two CTAs per SM, i.e. 8 stages in flight per SM (the kernel is bound by the TMA round trip).
+  constexpr uint32_t STAGE_BYTES = 3 * BST_TILE;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[ST], empty[ST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -229,7 +276,7 @@ tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
             ptx::mbar_expect_tx(&full[st], (uint32_t)(1 + chunks) * BST_TILE);
             ptx::tma_load_2d(stage, &maps.a, &full[st], 0, (int)(((long long)bh * p.blocks + blk) * 64));
             for (int c = 0; c < chunks; ++c)
-              ptx::tma_load_2d(stage + (2 + c) * BST_TILE, &maps.b, &full[st], h * p.head_state + c * 64, b * p.ctx_rows_b + in * 64);
+              ptx::tma_load_2d(stage + (1 + c) * BST_TILE, &maps.b, &full[st], h * p.head_state + c * 64, b * p.ctx_rows_b + in * 64);
           }
           __syncwarp();
         }
@@ -243,7 +290,7 @@ tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
                                            : ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, ptx::SWZ_128B);
     const uint32_t a_kstep16 = p.transpose_a ? (2048u >> 4) : 2u;
     // B = V tile [64 keys][head_state], MN-major SW128: 64-column atoms one tile apart, K=16 slice = 16 rows
-    const uint64_t b_desc0 = ptx::make_smem_desc(ptx::smem_u32(smem) + 2 * BST_TILE, BST_TILE, 1024, ptx::SWZ_128B);
+    const uint64_t b_desc0 = ptx::make_smem_desc(ptx::smem_u32(smem) + BST_TILE, BST_TILE, 1024, ptx::SWZ_128B);
     uint32_t sc = 0, n = 0;
     bool alive = true;
     for (long long it = blockIdx.x; it < total && alive; it += gridDim.x, ++n) {
@@ -358,9 +405,13 @@ inline int tc_bst_nt(int dtype, int c_dtype, int bsize, const int32_t* items, in
   BstNtParams p;
   p.items = items; p.n_items = n_items; p.lut_heads = lut_heads; p.batch = batch; p.heads = heads; p.blocks = blocks;
   p.head_state = head_state; p.ctx_rows_a = ctx_blks_a * 64; p.ctx_rows_b = ctx_blks_b * 64; p.c = c;
-  const size_t smem = (size_t)BST_STAGES * 3 * BST_TILE;
+  const unsigned long long c_rows = (unsigned long long)batch * heads * blocks * 64;
+  p.tma_store = (c_dtype != BSMM_F32 && c_rows < (1ull << 31)) ? 1 : 0;
+  if (p.tma_store) { if (int e = make_tmap_2d(&maps.c, c_dtype, c, 64, c_rows, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e; }
+  else maps.c = maps.a;
+  const size_t smem = (size_t)BST_NT_STAGES * 3 * BST_TILE + 4 * BST_TILE;
   const long long total = (long long)batch * heads * n_items;
-  const int sm = device_info().sm_count;
+  const int sm = 2 * device_info().sm_count;            // two CTAs per SM
   const int grid = (int)(total < sm ? total : sm);
   const bool bf = dtype == BSMM_BF16;
 #define BSMM_LAUNCH_NT(BFV, TCV)                                                         \
@@ -390,9 +441,9 @@ inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const i
   p.lut = lut; p.order = order; p.lut_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_c + blocks) : 0; p.n_out = ctx_blks_c; p.lut_heads = lut_heads;
   p.batch = batch; p.heads = heads; p.blocks = blocks; p.head_state = head_state;
   p.ctx_rows_b = ctx_blks_b * 64; p.ctx_rows_c = ctx_blks_c * 64; p.transpose_a = transpose_a; p.c = c;
-  const size_t smem = (size_t)BST_STAGES * 4 * BST_TILE;
+  const size_t smem = (size_t)BST_STAGES * 3 * BST_TILE;
   const long long total = (long long)batch * heads * ctx_blks_c;
-  const int sm = device_info().sm_count;
+  const int sm = 2 * device_info().sm_count;            // two CTAs per SM
   const int grid = (int)(total < sm ? total : sm);
   if (dtype == BSMM_BF16) {
     auto kern = tc_bst_xn_kernel<true>;
