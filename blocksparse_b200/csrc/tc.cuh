@@ -12,10 +12,10 @@
 // the A-operand collector hints (fill / use / lastuse): the B200 probe (profiles/r1_tc_probe.txt)
 // shows an N=32 MMA is shared-memory bound at 40 cycles when A is re-read, 16 + 27/R with reuse R.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0      TMA producer: activation tiles (4-stage ring) and W blocks (32-stage ring)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  epilogue: tcgen05.ld -> 16-bit -> swizzled smem staging -> TMA store
+// Warp roles (persistent over tiles, (2*NP + 4) warps, see the pipeline protocol below):
+//   warps 0..NP-1     TMA producers, one per pipeline (activation tile + W blocks of a group -> one mbarrier)
+//   warps NP..2NP-1   MMA issuers, one per pipeline (one elected thread each); the first also owns TMEM alloc
+//   last 4 warps      epilogue: tcgen05.ld -> 16-bit -> swizzled smem staging -> TMA store, then clear the lanes
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -60,12 +60,15 @@ inline int make_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t in
 // hint, merging of adjacent blocks into one wider MMA) is precomputed on the host into a 128-byte
 // group record, because the first profile (profiles/r1_xprop_v1_ncu.txt) showed both the producer and
 // the single issuing thread instruction-bound at hundreds of cycles per block when they derived them.
-//   producer warps (2, alternating groups): one coalesced 128-byte load per group, prefetched a group
-//     ahead; lanes 4..11 each issue one W TMA load; lanes 12..27 copy the run commands to smem
-//   MMA warp: one barrier wait per group, then one LDS.64 + one tcgen05.mma per run and K slice
-// OCC = CTAs per SM.  OCC 2 halves the output tile (256 TMEM columns, 8/4 blocks) so that two CTAs --
-// two independent MMA-issuing threads -- share one SM's tensor core: the issue rate of one thread
-// (~45 cycles per N=32 MMA, profiles/r1_xprop_v3_ncu.txt) is what bounds the single-CTA kernel.
+//   producer warp p (groups gc with gc % NP == p): one coalesced 128-byte load per group, prefetched a
+//     group ahead; lanes 4..11 each issue one W TMA load; lanes 12..19 write the run commands to smem
+//   issuer warp p (same groups): one barrier wait per group, LDS.128 commands, then one tcgen05.mma per
+//     run and K slice; the NP issuers take turns in group order (turn[] mbarriers) so results are deterministic
+// Pipeline p owns the stages with index % NP == p: every mbarrier has exactly one waiter that walks its phases
+// in order (with stages handed round-robin to whichever warp came next, a waiter two phases behind would pass
+// a parity test early).
+// OCC = CTAs per SM.  OCC 2 halves the output tile (256 TMEM columns) so that the epilogue of one CTA overlaps
+// the main loop of the other.
 // VAR 1 = "sparse" variant for layouts with ~1 W block per group (density <= ~12 %): 2 W slots per stage instead of
 // 8, which doubles the number of stages in flight -- at 5-10 % density the kernel is bound by the TMA round trip.
 template <int BS, int OCC, int VAR = 0> struct XpropCfg;
