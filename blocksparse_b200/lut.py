@@ -163,8 +163,8 @@ class MatmulLuts(object):
         self.bprop_rows, self.bprop_max = row_lut(b[0], b[1], b[2], CB)
         self._f, self._b = f, b
 
-    def updat_schedule(self, bsize, k_per_tile=None):
-        return build_updat_schedule(self.updat_lut, self.CB, self.KB, bsize, k_per_tile)
+    def updat_schedule(self, bsize, k_per_tile=None, n_cta=None):
+        return build_updat_schedule(self.updat_lut, self.CB, self.KB, bsize, k_per_tile, n_cta)
 
     def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None):
         outs, ins, wids = self._b if bprop else self._f
@@ -210,8 +210,8 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
       * W blocks are listed in accumulator order and staged in consecutive shared-memory slots, so
         blocks whose accumulators are adjacent form a *run* that is issued as ONE wider MMA
         (N = run_len*bsize); a dense layout degenerates to ordinary wide GEMM instructions;
-      * the accumulate flag of every run (0 = first touch of those accumulators in this tile) -- runs
-        are split where the flag changes;
+      * every run accumulates (bit 0 of int1 is always 1): the kernel's epilogue leaves the accumulators zeroed,
+        so no first-touch bookkeeping -- and no run split at a first touch -- is needed;
       * (the A-collector hint needs no field: the first run of a group fills the collector, the rest reuse it).
 
     int32 layout:
@@ -257,16 +257,13 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     g_count = np.diff(np.concatenate((g_first, [nnz])))
     pos_in_group = np.arange(nnz) - g_first[group_id]
 
-    # first touch of an accumulator slot inside its tile: earliest pair (in processing order) of (tile, slot)
-    key = tile_s * T + slot_s
-    first_idx = np.full(n_tiles * T, nnz, dtype=np.int64)
-    np.minimum.at(first_idx, key, np.arange(nnz))
-    accumulate = (np.arange(nnz) != first_idx[key]).astype(np.int64)
+    # accumulators start from zero (cleared by the epilogue), so every run accumulates
+    accumulate = np.ones(nnz, dtype=np.int64)
 
-    # runs: consecutive pairs of a group with consecutive slots and equal accumulate flag
+    # runs: consecutive pairs of a group with consecutive slots
     new_run = np.ones(nnz, dtype=bool)
     if nnz:
-        new_run[1:] = new_group[1:] | (slot_s[1:] != slot_s[:-1] + 1) | (accumulate[1:] != accumulate[:-1])
+        new_run[1:] = new_group[1:] | (slot_s[1:] != slot_s[:-1] + 1)
     run_first = np.nonzero(new_run)[0]
     run_len = np.diff(np.concatenate((run_first, [nnz])))
     run_group = group_id[run_first]
@@ -304,7 +301,38 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
 UPDAT_REC_INTS = 64      # one 256-byte record per updat tile
 
 
-def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None):
+def _updat_makespan(g_cnt, g_nwin, n_cta):
+    """Cost model of the persistent updat grid: a tile streams (128-feature X tile + n_act DY blocks) per K step, tiles are
+    dealt round-robin in decreasing-cost order; returns the busiest CTA's load."""
+    sizes = []
+    for c, w in zip(g_cnt.tolist(), g_nwin.tolist()):
+        if c:
+            q, r = divmod(c, w)
+            sizes += [q + 1] * r + [q] * (w - r)
+    cost = np.sort(4.0 + np.asarray(sizes, dtype=np.float64))[::-1]
+    load = np.zeros(n_cta)
+    np.add.at(load, np.arange(len(cost)) % n_cta, cost)
+    return load.max()
+
+
+def _balance_windows(g_cnt, g_nwin, KT, n_cta):
+    """More (smaller) windows than the minimum when that fills whole waves of the n_cta persistent CTAs."""
+    t_min = int(g_nwin[g_cnt > 0].sum())
+    best, best_cost = g_nwin, _updat_makespan(g_cnt, g_nwin, n_cta)
+    target = -(-t_min // n_cta) * n_cta
+    while target <= 1.35 * t_min + 1 and target <= int(g_cnt.sum()):
+        nw = g_nwin.copy()
+        for _ in range(target - t_min):                    # split the group with the widest windows once more
+            g = int(np.argmax(np.where(nw < g_cnt, g_cnt / nw, 0.0)))
+            nw[g] += 1
+        c = _updat_makespan(g_cnt, nw, n_cta)
+        if c < best_cost - 1e-9:
+            best, best_cost = nw, c
+        target += n_cta
+    return best
+
+
+def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None, n_cta=None):
     """Schedule for the tcgen05 updat kernel (csrc/tc_updat.cuh): a "gathered dense GEMM".
 
     A tile pairs a GROUP of 128/bsize consecutive input blocks (128 features = the MMA M axis) with up
@@ -330,8 +358,22 @@ def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None):
     lut = np.asarray(updat_lut, dtype=np.int64).reshape(-1, 2)
     cs, ks = lut[:, 0], lut[:, 1]
     wid = np.arange(len(cs), dtype=np.int64)
-    grp, win = cs // G, ks // KT
-    n_win = ceil_div(KB, KT)
+    # Windows are cut from each group's KEPT output blocks (those with at least one active block in the group), split
+    # evenly into ceil(n_kept / KT) windows: tiles come out (nearly) full -- N = 256 MMAs, the activation tile
+    # re-read n_kept/KT times instead of KB/KT times -- and of almost equal cost.
+    grp = cs // G
+    n_grp = ceil_div(CB, G)
+    gk = np.unique(grp * KB + ks)                         # distinct (group, k), sorted by group then k
+    g_of, k_of = gk // KB, gk % KB
+    g_first = np.searchsorted(g_of, np.arange(n_grp))     # first kept entry of each group
+    g_cnt = np.diff(np.concatenate((g_first, [len(gk)])))
+    g_nwin = np.maximum(1, -(-g_cnt // KT))
+    if n_cta:
+        g_nwin = _balance_windows(g_cnt, g_nwin, KT, int(n_cta))
+    pos = np.arange(len(gk)) - g_first[g_of]              # rank of k among the group's kept blocks
+    win_of_gk = (pos * g_nwin[g_of]) // np.maximum(g_cnt[g_of], 1)     # even split: sizes differ by at most 1
+    n_win = int(g_nwin.max()) if len(gk) else 1
+    win = win_of_gk[np.searchsorted(gk, grp * KB + ks)]
     tile_key = grp * n_win + win
     # distinct (tile, k) pairs -> compact slot numbers
     tk = tile_key * KB + ks

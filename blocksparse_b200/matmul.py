@@ -125,7 +125,7 @@ class BlocksparseMatMul(object):
             if tb:
                 d["xprop_sched"] = {}          # (bprop, n_tiles) -> (tensor, n_tiles, groups_off), built on demand
                 d["cta_slots"] = torch.cuda.get_device_properties(device).multi_processor_count * _OCC[self.bsize]
-                us, uoff = self._luts.updat_schedule(self.bsize)
+                us, uoff = self._luts.updat_schedule(self.bsize, n_cta=torch.cuda.get_device_properties(device).multi_processor_count)
                 d["updat_sched"] = torch.as_tensor(us, device=device)
                 d["updat_tiles"], d["updat_kt"] = int(us[0]), int(us[2])
             self._dev[key] = d
