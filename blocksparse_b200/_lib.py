@@ -27,6 +27,7 @@ SIGNATURES = {
     "bsmm_updat": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i,
                         _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "bsmm_gate_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "bsmm_gate_weights": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "bst_nt": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "bst_xn": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "bst_softmax": (_i, [_i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),

@@ -131,6 +131,19 @@ int bsmm_gate_grad(int dtype, int bsize, int blocks, const void* dw, const void*
   return check_launch("gate_grad");
 }
 
+int bsmm_gate_weights(int dtype, int bsize, int blocks, const void* w, const float* gate, void* w_out, void* stream) {
+  if (!w || !gate || !w_out || blocks <= 0) return fail(BSMM_E_ARG, "bsmm_gate_weights: bad arguments");
+  if (int e = check_bsize_axis(bsize, 0)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)blocks * bsize * bsize;
+  const int threads = 256;
+  const long long grid = (total / 2 + threads - 1) / threads;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    gate_weights_kernel<T><<<(unsigned)grid, threads, 0, s>>>((const T*)w, gate, (T*)w_out, total, bsize * bsize);
+  });
+  return check_launch("gate_weights");
+}
+
 // ---------------------------------------------------------------------------------------
 static int check_bst(int bsize, int lut_heads, int heads, int head_state, int batch, int blocks) {
   if (bsize != 8 && bsize != 16 && bsize != 32 && bsize != 64)

@@ -282,4 +282,16 @@ __global__ void gate_grad_kernel(const T* __restrict__ dw, const T* __restrict__
   if (lane == 0) dg[blk] = s;
 }
 
+// w_out[w] = gate[w] * w[w]  (a zero gate gives an exact zero block).  Lets a gated fprop / bprop of 16-bit weights run
+// on the tcgen05 kernel: the reference's gated tensor-core kernels also scale the loaded 16-bit weights by the gate.
+template <typename T>
+__global__ void gate_weights_kernel(const T* __restrict__ w, const float* __restrict__ gate, T* __restrict__ out,
+                                    long long total, int elems) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= total) return;
+  const float g = gate[i / elems];
+  out[i] = from_f32<T>(to_f32<T>(w[i]) * g);            // elems is even: both elements belong to the same block
+  out[i + 1] = from_f32<T>(to_f32<T>(w[i + 1]) * g);
+}
+
 }  // namespace bsmm

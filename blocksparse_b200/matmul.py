@@ -177,6 +177,13 @@ class BlocksparseMatMul(object):
         y2 = torch.empty((feat_out, N) if self.axis == 0 else (N, feat_out), dtype=x.dtype, device=x.device)
         if gate is not None:
             gate = gate.to(torch.float32).contiguous()
+            if sched is not None and x.dtype != torch.float32 and not (flags & _lib.FLAG_FORCE_GENERIC):
+                # gated product on the tcgen05 kernel: fold the gate into a scaled copy of the (small) weight tensor,
+                # as the reference's gated kernels do with the loaded weights (cn_64.cu:96-98)
+                wg = torch.empty_like(w)
+                _lib.check(lib.bsmm_gate_weights(_lib.dtype_code(w.dtype), self.bsize, self.blocks, w.data_ptr(),
+                                                 gate.data_ptr(), wg.data_ptr(), _lib.stream_ptr()), "bsmm_gate_weights")
+                w, gate = wg, None
         rc = lib.bsmm_xprop(_lib.dtype_code(x.dtype), self.axis, self.bsize, int(bprop),
                             lut.data_ptr(), n_out, n_in, self.blocks,
                             x2.data_ptr(), w.data_ptr(), y2.data_ptr(), N,

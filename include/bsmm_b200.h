@@ -12,6 +12,7 @@
  *   bsmm_updat            <- hgemm_blocksparse_nt_{64,128}_dds / hgemm_blocksparse_tn_dds /
  *                            BsmmUpdat_CN   (src/blocksparse_matmul_op.cc:223-311)
  *   bsmm_gate_grad        <- BlocksparseGateGrad (src/blocksparse_matmul_op.cc:490-540)
+ *   bsmm_gate_weights     <- the gate scaling inside the reference's gated xprop kernels (cn_64.cu:96-98)
  *   bst_nt                <- bst_hgemm_nt / bst_sgemm_nt   (src/bst_op.cc:139-144,183-250)
  *   bst_xn                <- bst_hgemm_xn / bst_sgemm_xn   (src/bst_op.cc:251-320)
  *   bst_softmax           <- BlocksparseMaskedSoftmax<T,V> (src/bst_op.cc:331-340,374-428)
@@ -124,6 +125,12 @@ int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
 /* dg[w] = sum_ij dw[w][i][j] * w[w][i][j]   (BlocksparseMatmulDG, op.cc:490-540) */
 int bsmm_gate_grad(int dtype, int bsize, int blocks, const void* dw, const void* w,
                    float* dg, void* stream);
+
+/* w_out[w] = gate[w] * w[w] (zero gate => exact zero block).  Host layers call it before a gated bsmm_xprop of 16-bit
+ * weights so that the gated product runs on the tcgen05 kernel: the reference's gated kernels apply the gate to the
+ * loaded weights the same way (cn_64.cu:96-98, blocksparse_hgemm_nc_op_gpu.cu gate handling). */
+int bsmm_gate_weights(int dtype, int bsize, int blocks, const void* w, const float* gate,
+                      void* w_out, void* stream);
 
 /* ---- block-sparse transformer ------------------------------------------------------ */
 

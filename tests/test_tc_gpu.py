@@ -80,6 +80,34 @@ def test_tc_xprop_repeatable_and_stream_ordered():
         assert torch.equal(y, y0)          # no atomics, no races: bit-identical run to run
 
 
+@pytest.mark.parametrize("bs", [32, 64])
+def test_gated_xprop_runs_on_tcgen05(bs):
+    """gate folded into a scaled weight copy (bsmm_gate_weights) + tcgen05 kernel == oracle's gated product;
+    zero gates drop their blocks exactly."""
+    rng = np.random.default_rng(11)
+    lay = layout(rng, 12, 10, 0.4)
+    bsmm = BlocksparseMatMul(lay, block_size=bs, feature_axis=1)
+    orc = MatmulOracle(lay, 32, 1)
+    orc.bsize, orc.C, orc.K, orc.w_shape = bs, 12 * bs, 10 * bs, bsmm.w_shape
+    N = 200
+    W = torch.as_tensor(rng.normal(0, 0.1, bsmm.w_shape).astype(np.float32)).bfloat16()
+    X = torch.as_tensor(rng.normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).bfloat16()
+    E = torch.as_tensor(rng.normal(0, 1, bsmm.o_shape(N)).astype(np.float32)).bfloat16()
+    gate = rng.uniform(0.5, 1.5, bsmm.blocks).astype(np.float32)
+    gate[rng.random(bsmm.blocks) < 0.3] = 0.0
+    Wg = (W.float().numpy() * gate[:, None, None])
+    g = torch.as_tensor(gate).cuda()
+    y = bsmm.fprop(X.cuda(), W.cuda(), gate=g)
+    assert _lib.last_kernel().startswith("tcgen05_xprop")
+    dx = bsmm.bprop(E.cuda(), W.cuda(), gate=g)
+    assert _lib.last_kernel().startswith("tcgen05_xprop") and _lib.device_error() == 0
+    for got, ref in [(y, orc.fprop_dense(X.float().numpy(), Wg)), (dx, orc.bprop_dense(E.float().numpy(), Wg))]:
+        err = np.abs(got.float().cpu().numpy() - ref)
+        assert err.max() <= 4e-2 * np.abs(ref).max() and np.sqrt((err ** 2).sum() / (ref ** 2).sum()) <= 1e-2
+    yg = bsmm.fprop(X.cuda(), W.cuda(), gate=g, flags=_lib.FLAG_FORCE_GENERIC)      # CUDA-core gated path agrees
+    assert (y.float() - yg.float()).abs().max().item() <= 2.0 ** -6 * yg.float().abs().max().item()
+
+
 UPDAT_CASES = [
     # CB, KB, density, N, bs, pairs
     (8, 8, 0.3, 128, 32, 1),
