@@ -38,6 +38,36 @@ def make_layout(density, cb=C // BS, kb=K // BS, seed=SEED):
     return lay
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs local to GPU `index` (sysfs local_cpulist of its PCI device); returns the previous
+    affinity mask, or None when the topology cannot be read (then nothing changes)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                   # NVML pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus or cpus == old:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -300,6 +330,9 @@ def main():
                  "algorithmic_flops_per_launch": flops_op, "algorithmic_bytes_per_launch": bytes_op})
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    # pinned buffers are first-touched on the NUMA node the GPU hangs off (PCIe copies from the far socket run at about
+    # half rate on these hosts); the affinity is restored afterwards
+    old_affinity = bind_to_gpu_numa_node(dev.index if dev.index is not None else 0)
     hx = [torch.empty(bsmm.i_shape(N), dtype=dtype).pin_memory() for _ in range(2)]
     he = [torch.empty(bsmm.o_shape(N), dtype=dtype).pin_memory() for _ in range(2)]
     for h, s in zip(hx + he, Xs[:2] + Es[:2]):
@@ -308,6 +341,8 @@ def main():
     hdx = torch.empty(bsmm.i_shape(N), dtype=dtype).pin_memory()
     hdw = torch.empty(bsmm.w_shape, dtype=dtype).pin_memory()
     w_param = W.clone().requires_grad_()
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)
 
     # Three streams pipeline consecutive steps (copies of step i+1 / i-1 overlap the kernels of step i, as a training
     # input pipeline would); every step still moves its own inputs H2D and its own results D2H inside the timed region.
@@ -374,7 +409,7 @@ def main():
     e2e = {"value": flops_step_gpu * world / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
            "h2d_bytes_per_step": int(hx[0].numel() * 2 + he[0].numel() * 2),
            "d2h_bytes_per_step": int(hy.numel() * 2 + hdx.numel() * 2 + hdw.numel() * 2),
-           "ms_per_step": e2e_ms,
+           "ms_per_step": e2e_ms, "host_buffers_numa_local": old_affinity is not None,
            "api": "BlocksparseMatMul.__call__ + autograd backward; pinned host buffers; H2D / kernels / D2H on three streams, double-buffered"}
 
     sweep = None
