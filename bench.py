@@ -251,7 +251,10 @@ def main():
         dx = bsmm.bprop(e, W)
         dw = bsmm.updat([x], [e])
         launches[0] += 3
-        bdist.allreduce_dw(dw)                 # no-op at world size 1
+        # dW all-reduce (no-op at world size 1).  Issued on the side stream or with async_op it takes the same ~47 us per
+        # step at N=2 (tools/diag_dist.py, profiles/r1_dist_diag.txt): the persistent kernels occupy every SM, so the NCCL
+        # kernel runs between them either way.
+        bdist.allreduce_dw(dw)
         return y, dx, dw
 
     def barrier():

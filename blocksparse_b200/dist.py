@@ -52,6 +52,7 @@ class AllreduceStream(object):
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             dist.all_reduce(dw)
+        dw.record_stream(self.stream)          # allocated on the compute stream, consumed on this one
         self.pending.append(dw)
         return dw
 
