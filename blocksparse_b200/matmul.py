@@ -6,6 +6,7 @@ operates on torch tensors and calls the sm_100a kernels through the C ABI in
 include/bsmm_b200.h.  There is no CPU path: tensors must live on a CUDA device.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -13,15 +14,12 @@ import torch
 from . import _lib
 from .lut import MatmulLuts, pick_tile_count
 
-# tcgen05 tile width (output blocks whose accumulators share one CTA's tensor memory)
-import os
-
 # Output blocks per xprop tile and CTAs per SM (csrc/tc.cuh XpropCfg<BS, OCC>), picked from B200 timings
 # (profiles/r1_xprop_tuning.txt): 32x32 blocks run best as half-width tiles (8 blocks = 256 TMEM columns) with two
 # CTAs per SM, 64x64 blocks as full-width tiles (8 blocks = 512 columns) with one.  BSMM_XPROP_OCC=1|2 forces one.
 _OCC_ENV = os.environ.get("BSMM_XPROP_OCC", "")
 _OCC = {32: 2, 64: 1} if _OCC_ENV not in ("1", "2") else {32: int(_OCC_ENV), 64: int(_OCC_ENV)}
-_WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))
+_WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))     # tuning aid: force the W-slots-per-stage variant (2 or 4)
 _TILE_BLOCKS = {bs: (256 if occ == 2 else 512) // bs for bs, occ in _OCC.items()}
 # W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
 _W_PER_GROUP = {32: 8, 64: 2 if _OCC[64] == 2 else 4}

@@ -206,6 +206,39 @@ def test_updat_schedule_covers_every_block_once(bsize):
         assert len(seen) == L.blocks
 
 
+def test_updat_schedule_balances_whole_waves():
+    """With a CTA count the window split trades a few more tiles for whole waves; coverage and compaction stay intact."""
+    from blocksparse_b200.lut import _updat_makespan
+    rng = np.random.default_rng(5)
+    lay = (rng.random((128, 128)) < 0.25).astype(np.int32)
+    L = MatmulLuts(lay)
+    base, _ = L.updat_schedule(32)
+    bal, off = L.updat_schedule(32, n_cta=148)
+    nb, nl = int(base[0]), int(bal[0])
+    assert nl >= nb and nl % 148 == 0                       # 370 -> 444 tiles = three full waves
+    rec = bal[off:].reshape(nl, 64)
+    cost = lambda r: np.sort(4.0 + r[:, 1].astype(float))[::-1]
+    def makespan(r):
+        load = np.zeros(148)
+        np.add.at(load, np.arange(len(r)) % 148, cost(r))
+        return load.max()
+    assert makespan(rec) < makespan(base[off:].reshape(nb, 64))
+    seen = set()
+    for t in range(nl):
+        n_act = rec[t, 1]
+        assert 1 <= n_act <= 8
+        for sl in range(n_act):
+            ws = [int(rec[t, 16 + i * 8 + sl]) for i in range(4) if rec[t, 16 + i * 8 + sl] >= 0]
+            assert ws and not (set(ws) & seen)
+            seen.update(ws)
+    assert len(seen) == L.blocks
+    # a layout that already fills its waves, or a tiny one, is left alone
+    tiny = MatmulLuts(np.ones((4, 4), dtype=np.int32))
+    a, _ = tiny.updat_schedule(32)
+    b, _ = tiny.updat_schedule(32, n_cta=148)
+    assert np.array_equal(a, b)
+
+
 def test_pick_tile_count_fills_whole_waves():
     from blocksparse_b200.lut import pick_tile_count
     # BASELINE cfg 2 on a B200 with two CTAs per SM: 32 minibatch tiles, 128 output blocks, 296 CTA slots

@@ -1,12 +1,7 @@
 #!/bin/bash
+# Quick GPU iteration: tcgen05 parity tests, then per-op timings at BASELINE cfg 2 and the attention ops of cfg 3.
 mkdir -p gpurun_out
-timeout 600 python bench.py --gpus 1 --steps 100 --warmup 5 > gpurun_out/bench1.txt 2>&1; echo "rc=$?"
-python - <<'PY'
-import json
-l=[x for x in open('gpurun_out/bench1.txt') if x.startswith('{')]
-if l:
-    d=json.loads(l[-1]); print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']); print('cpu',d['cpu_baseline'])
-else:
-    print(open('gpurun_out/bench1.txt').read()[-3000:])
-PY
-cat /sys/bus/pci/devices/*/local_cpulist 2>/dev/null | sort | uniq -c | head -5; nvidia-smi topo -m 2>/dev/null | head -8
+timeout 900 python -m pytest tests/test_tc_gpu.py -x -q > gpurun_out/pytest_tc.txt 2>&1; rc=$?; tail -2 gpurun_out/pytest_tc.txt
+if [ $rc -ne 0 ]; then tail -30 gpurun_out/pytest_tc.txt; exit 1; fi
+timeout 300 python tools/time_ops.py 0.05 0.10 0.25 0.5 1.0 2>&1 | tee gpurun_out/time_ops.txt
+timeout 300 python tools/bench_bst.py 2>&1 | cut -c1-200 | tee gpurun_out/bench_bst.txt
