@@ -2,7 +2,7 @@
 // GEMM and measures issue throughput of small-N MMAs (the block-sparse case) on a B200.
 // Every wait is bounded, so a protocol error prints TIMEOUT instead of hanging the GPU.
 //
-//   tools/tc_probe <test>     test in {ss_kk, ss_kmn, tma_kk, tma_mnk, ts_st, ts_cp, bench}
+//   tools/tc_probe <test>     test in {ss_kk, ss_kmn, tma_kk, tma_mnk, ts_st, ts_cp, ss16_kk, ss16_kmn, bench}
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -118,6 +118,56 @@ __global__ void __launch_bounds__(128) probe_gemm(int test, const bf16* Ag, cons
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, 64);
+}
+
+// ----------------------------------------------------------------------------------------------
+// 16 x 16 blocks (SWIZZLE_32B operands, 32-byte rows): D[128 x 32] = A[128 x 16] * [B0 | B1] where B0, B1 are two
+// 16 x 16 blocks staged 512 bytes apart and issued as ONE N = 32 MMA (the merged-run case of the xprop kernel).
+//   b_mn = 0: blocks stored [n][k] (K-major, bprop);  b_mn = 1: blocks stored [k][n] (MN-major, fprop).
+__host__ __device__ inline uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
+
+__global__ void __launch_bounds__(128) probe_gemm16(int b_mn, const bf16* Ag, const bf16* Bg, float* Dg, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;              // 128 rows x 32 B = 4 KB
+  uint8_t* sB = smem + 4096;       // 2 blocks x 512 B
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid / 32;
+  if (tid == 0) { ptx::mbar_init(&bar_mma, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base_s, 32); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  for (int i = tid; i < 128 * 16; i += 128) {
+    const int m = i / 16, k = i % 16;
+    *reinterpret_cast<bf16*>(sA + swz32(m * 32 + k * 2)) = Ag[m * 16 + k];
+  }
+  for (int i = tid; i < 2 * 16 * 16; i += 128) {
+    const int blk = i / 256, r = (i % 256) / 16, c = i % 16;      // block-local row-major 16 x 16, 32-byte rows
+    *reinterpret_cast<bf16*>(sB + blk * 512 + swz32(r * 32 + c * 2)) = Bg[i];
+  }
+  ptx::fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t idesc = ptx::make_idesc_f16(true, false, b_mn != 0, 128, 32);
+    const uint64_t adesc = ptx::make_smem_desc(ptx::smem_u32(sA), 16, 256, ptx::SWZ_32B);
+    // K-major B: the second block continues the N rows (two more 8-row groups, SBO apart).  MN-major B: the second
+    // block is the next 16-element N atom, LBO = 512 bytes away.
+    const uint64_t bdesc = b_mn ? ptx::make_smem_desc(ptx::smem_u32(sB), 512, 256, ptx::SWZ_32B)
+                                : ptx::make_smem_desc(ptx::smem_u32(sB), 16, 256, ptx::SWZ_32B);
+    ptx::mma_ss(tmem, adesc, bdesc, idesc, 0);
+    ptx::tc_commit(&bar_mma);
+  }
+  if (!ptx::mbar_wait(&bar_mma, 0)) { if (tid == 0) status[0] = 2; }
+  ptx::tc_fence_after();
+  uint32_t r[32];
+  ptx::tmem_ld_x32(tmem + ((uint32_t)(warp * 32) << 16), r);
+  ptx::tmem_ld_wait();
+  for (int j = 0; j < 32; ++j) Dg[tid * 32 + j] = __uint_as_float(r[j]);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 32);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -260,6 +310,44 @@ static int run_gemm(int test, const char* name) {
   return (status == 0 && maxerr < 1e-3) ? 0 : 1;
 }
 
+static int run_gemm16(int b_mn, const char* name) {
+  std::vector<float> A(128 * 16), B(16 * 32);             // A[m][k], B[k][n] logical with n = 0..31 over two blocks
+  srand(4321 + b_mn);
+  for (auto& v : A) v = (float)((rand() % 17) - 8) / 8.f;
+  for (auto& v : B) v = (float)((rand() % 13) - 6) / 4.f;
+  std::vector<bf16> Ah(128 * 16), Bh(2 * 256);
+  for (int i = 0; i < 128 * 16; ++i) Ah[i] = __float2bfloat16(A[i]);
+  for (int blk = 0; blk < 2; ++blk)
+    for (int k = 0; k < 16; ++k)
+      for (int n = 0; n < 16; ++n) {
+        const float v = B[k * 32 + blk * 16 + n];
+        if (b_mn) Bh[blk * 256 + k * 16 + n] = __float2bfloat16(v);      // [k][n]
+        else      Bh[blk * 256 + n * 16 + k] = __float2bfloat16(v);      // [n][k]
+      }
+  bf16 *Ad, *Bd; float* Dd; int* st;
+  CK(cudaMalloc(&Ad, Ah.size() * 2)); CK(cudaMalloc(&Bd, Bh.size() * 2)); CK(cudaMalloc(&Dd, 128 * 32 * 4)); CK(cudaMalloc(&st, 4));
+  CK(cudaMemcpy(Ad, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(Bd, Bh.data(), Bh.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(Dd, 0, 128 * 32 * 4)); CK(cudaMemset(st, 0, 4));
+  probe_gemm16<<<1, 128, 8192>>>(b_mn, Ad, Bd, Dd, st);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-8s LAUNCH ERROR %s\n", name, cudaGetErrorString(e)); return 1; }
+  std::vector<float> D(128 * 32); int status = 0;
+  CK(cudaMemcpy(D.data(), Dd, D.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&status, st, 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 32; ++n) {
+      double r = 0;
+      for (int k = 0; k < 16; ++k) r += (double)A[m * 16 + k] * (double)B[k * 32 + n];
+      maxerr = fmax(maxerr, fabs(r - D[m * 32 + n]));
+      maxref = fmax(maxref, fabs(r));
+    }
+  printf("%-8s status=%d max_abs_err=%.4g (max |ref| %.3g) %s\n", name, status, maxerr, maxref,
+         (status == 0 && maxerr < 1e-3) ? "PASS" : "FAIL");
+  return (status == 0 && maxerr < 1e-3) ? 0 : 1;
+}
+
 template <int MODE, int N, int REUSE>
 static void bench_one(const char* name, long long* cyc, int* st) {
   const int iters = 256;
@@ -316,6 +404,8 @@ int main(int argc, char** argv) {
   if (!strcmp(t, "tma_mnk")) return run_gemm(T_TMA_MNK, t);
   if (!strcmp(t, "ts_st")) return run_gemm(T_TS_ST, t);
   if (!strcmp(t, "ts_cp")) return run_gemm(T_TS_CP, t);
+  if (!strcmp(t, "ss16_kk")) return run_gemm16(0, t);       // 16x16 blocks, SWIZZLE_32B, K-major B (not yet run on a B200)
+  if (!strcmp(t, "ss16_kmn")) return run_gemm16(1, t);      // 16x16 blocks, SWIZZLE_32B, MN-major B
   if (!strcmp(t, "bench")) { run_bench(); return 0; }
   printf("unknown test %s\n", t);
   return 2;
