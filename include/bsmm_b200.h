@@ -93,9 +93,11 @@ int         bsmm_device_error(void);
  * sched: optional tile schedule for the tcgen05 kernels built by the host layer
  *    (blocksparse_b200/lut.py:build_tile_schedule, device memory) with its shape passed by value:
  *    sched_tiles output tiles of (sched_tile_blocks & 0xff) consecutive output blocks each (bits 8.. = W blocks
- *    per schedule group when it differs from the default, selecting the deep-pipeline "sparse" variant), group records
- *    starting at int32 index sched_groups_off; NULL selects the CUDA-core kernels.
- * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).
+ *    per schedule group when it differs from the default: 2 or 4 select the deeper-pipeline variants used for
+ *    layouts below ~12 % / ~37 % density), group records starting at int32 index sched_groups_off; NULL selects
+ *    the CUDA-core kernels.
+ * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).  With a gate the call runs on the
+ *    CUDA-core kernels; for 16-bit weights call bsmm_gate_weights first and pass gate = NULL to stay on tcgen05.
  */
 int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
                const int32_t* lut, int n_out, int n_in, int blocks,
