@@ -143,7 +143,7 @@ def cpu_reference(density, axis, budget_s=20.0, steps=1):
     lay = make_layout(density)
     orc = MatmulOracle(lay, BS, axis)
     rng = np.random.default_rng(SEED)
-    n = 1024                                 # columns of the 4096-wide minibatch timed per step
+    n = 1024                                 # columns of the 4096-wide minibatch timed per step (shrunk below for many steps)
     W = rng.normal(0, 0.01, orc.w_shape).astype(np.float32)
     X = rng.normal(0, 0.1, orc.i_shape(n)).astype(np.float32)
     E = rng.normal(0, 0.1, orc.o_shape(n)).astype(np.float32)
@@ -176,6 +176,19 @@ def cpu_reference(density, axis, budget_s=20.0, steps=1):
         limiter = threadpool_limits(limits=threads)
     except Exception:
         pass
+    # `--impl reference --steps K`: every step is one pass over a column sample sized so that the K steps end within
+    # ~2 minutes (the metric is a rate, so the sample size only changes BLAS efficiency a little); the default
+    # cpu_baseline leg (steps == 1) keeps the 1024-column sample and repeats it 3 times.
+    if steps > 3:
+        xs = X[:128] if axis else X[:, :128]
+        es = E[:128] if axis else E[:, :128]
+        t = time.perf_counter()
+        one_pass(xs, es)
+        per_col = (time.perf_counter() - t) / 128
+        n_fit = int(120.0 / (steps * per_col))
+        n = max(64, min(1024, n_fit // 64 * 64))
+        X = X[:n] if axis else X[:, :n]
+        E = E[:n] if axis else E[:, :n]
     t0 = time.perf_counter()
     done = 0
     while done < steps or (time.perf_counter() - t0 < budget_s and done < 3):
