@@ -69,6 +69,13 @@ def check(rc, what):
         raise BsmmError("%s failed (cuda error %d): %s" % (what, rc, msg))
 
 
+def grid_sms(device):
+    """SMs the persistent kernels are sized for: the device's SM count minus BSMM_SM_MARGIN (see csrc/common.cuh)."""
+    import torch
+    margin = max(0, int(os.environ.get("BSMM_SM_MARGIN", "0") or 0))
+    return max(1, torch.cuda.get_device_properties(device).multi_processor_count - margin)
+
+
 def device_error():
     """Synchronise and return (then clear) the sticky device-side error word; 0 means no kernel timed out."""
     return load().bsmm_device_error()

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libbsmm_b200.so (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -63,16 +64,28 @@ __host__ __device__ inline int dtype_size(int dt) { return dt == BSMM_F32 ? 4 : 
     default: return bsmm::fail(BSMM_E_BSIZE, "unsupported block size %d", (int)(bs)); \
   }
 
-struct DeviceInfo { int sm_count, cc_major, cc_minor; bool ok; };
+// sm_grid = SMs the persistent tcgen05 grids are sized for: sm_count minus BSMM_SM_MARGIN (environment, default 0).
+// A margin leaves SMs free for a concurrent NCCL kernel: with every SM taken by persistent CTAs an all-reduce can only
+// run between kernels (profiles/r1_dist_diag.txt).
+struct DeviceInfo { int sm_count, cc_major, cc_minor; bool ok; int sm_grid; };
+inline int sm_margin() {
+  static const int margin = [] {
+    const char* e = getenv("BSMM_SM_MARGIN");
+    const int v = e ? atoi(e) : 0;
+    return v < 0 ? 0 : v;
+  }();
+  return margin;
+}
 inline const DeviceInfo& device_info() {
-  static thread_local DeviceInfo info = {0, 0, 0, false};
+  static thread_local DeviceInfo info = {0, 0, 0, false, 0};
   static thread_local int cached_dev = -1;
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) { info.ok = false; return info; }
   if (dev != cached_dev) {
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
-      info = {p.multiProcessorCount, p.major, p.minor, true};
+      const int usable = p.multiProcessorCount - sm_margin();
+      info = {p.multiProcessorCount, p.major, p.minor, true, usable > 0 ? usable : 1};
       cached_dev = dev;
     } else {
       info.ok = false;

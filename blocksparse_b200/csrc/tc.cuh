@@ -509,25 +509,25 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
     return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
                 p.n_ktiles, tile_blocks, n_out);
   if (occ == 2 && bsize == 32 && w_per_group == 4) {
-    return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 3>(p, maps, dev.sm_count, s)
-                              : launch_tc_xprop<32, false, 2, 3>(p, maps, dev.sm_count, s);
+    return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 3>(p, maps, dev.sm_grid, s)
+                              : launch_tc_xprop<32, false, 2, 3>(p, maps, dev.sm_grid, s);
   }
   if (w_per_group != 0 && !(bsize == 32 && occ == 2 && w_per_group == 2) &&
       w_per_group != (bsize == 32 ? 8 : (occ == 2 ? 2 : 4)))
     return fail(BSMM_E_ARG, "bsmm_xprop: schedule built with %d W blocks per group, no kernel variant matches", w_per_group);
   if (occ == 2 && bsize == 32 && w_per_group == 2)
-    return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 1>(p, maps, dev.sm_count, s)
-                              : launch_tc_xprop<32, false, 2, 1>(p, maps, dev.sm_count, s);
+    return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 1>(p, maps, dev.sm_grid, s)
+                              : launch_tc_xprop<32, false, 2, 1>(p, maps, dev.sm_grid, s);
   if (occ == 2) {
-    if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2>(p, maps, dev.sm_count, s)
-                                               : launch_tc_xprop<32, false, 2>(p, maps, dev.sm_count, s);
-    return dtype == BSMM_BF16 ? launch_tc_xprop<64, true, 2>(p, maps, dev.sm_count, s)
-                              : launch_tc_xprop<64, false, 2>(p, maps, dev.sm_count, s);
+    if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2>(p, maps, dev.sm_grid, s)
+                                               : launch_tc_xprop<32, false, 2>(p, maps, dev.sm_grid, s);
+    return dtype == BSMM_BF16 ? launch_tc_xprop<64, true, 2>(p, maps, dev.sm_grid, s)
+                              : launch_tc_xprop<64, false, 2>(p, maps, dev.sm_grid, s);
   }
-  if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 1>(p, maps, dev.sm_count, s)
-                                             : launch_tc_xprop<32, false, 1>(p, maps, dev.sm_count, s);
-  return dtype == BSMM_BF16 ? launch_tc_xprop<64, true, 1>(p, maps, dev.sm_count, s)
-                            : launch_tc_xprop<64, false, 1>(p, maps, dev.sm_count, s);
+  if (bsize == 32) return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 1>(p, maps, dev.sm_grid, s)
+                                             : launch_tc_xprop<32, false, 1>(p, maps, dev.sm_grid, s);
+  return dtype == BSMM_BF16 ? launch_tc_xprop<64, true, 1>(p, maps, dev.sm_grid, s)
+                            : launch_tc_xprop<64, false, 1>(p, maps, dev.sm_grid, s);
 }
 
 }  // namespace bsmm

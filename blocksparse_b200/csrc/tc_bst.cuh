@@ -411,7 +411,7 @@ inline int tc_bst_nt(int dtype, int c_dtype, int bsize, const int32_t* items, in
   else maps.c = maps.a;
   const size_t smem = (size_t)BST_NT_STAGES * 3 * BST_TILE + 4 * BST_TILE;
   const long long total = (long long)batch * heads * n_items;
-  const int sm = 2 * device_info().sm_count;            // two CTAs per SM
+  const int sm = 2 * device_info().sm_grid;             // two CTAs per SM
   const int grid = (int)(total < sm ? total : sm);
   const bool bf = dtype == BSMM_BF16;
 #define BSMM_LAUNCH_NT(BFV, TCV)                                                         \
@@ -443,7 +443,7 @@ inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const i
   p.ctx_rows_b = ctx_blks_b * 64; p.ctx_rows_c = ctx_blks_c * 64; p.transpose_a = transpose_a; p.c = c;
   const size_t smem = (size_t)BST_STAGES * 3 * BST_TILE;
   const long long total = (long long)batch * heads * ctx_blks_c;
-  const int sm = 2 * device_info().sm_count;            // two CTAs per SM
+  const int sm = 2 * device_info().sm_grid;             // two CTAs per SM
   const int grid = (int)(total < sm ? total : sm);
   if (dtype == BSMM_BF16) {
     auto kern = tc_bst_xn_kernel<true>;

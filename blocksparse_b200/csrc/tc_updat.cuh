@@ -283,11 +283,11 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   const bool bf = dtype == BSMM_BF16;
   const bool f32out = dw_dtype == BSMM_F32;
   if (bsize == 32) {
-    if (f32out) return bf ? launch_tc_updat<32, true, float>(p, maps, dev.sm_count, s) : launch_tc_updat<32, false, float>(p, maps, dev.sm_count, s);
-    return bf ? launch_tc_updat<32, true, __nv_bfloat16>(p, maps, dev.sm_count, s) : launch_tc_updat<32, false, __half>(p, maps, dev.sm_count, s);
+    if (f32out) return bf ? launch_tc_updat<32, true, float>(p, maps, dev.sm_grid, s) : launch_tc_updat<32, false, float>(p, maps, dev.sm_grid, s);
+    return bf ? launch_tc_updat<32, true, __nv_bfloat16>(p, maps, dev.sm_grid, s) : launch_tc_updat<32, false, __half>(p, maps, dev.sm_grid, s);
   }
-  if (f32out) return bf ? launch_tc_updat<64, true, float>(p, maps, dev.sm_count, s) : launch_tc_updat<64, false, float>(p, maps, dev.sm_count, s);
-  return bf ? launch_tc_updat<64, true, __nv_bfloat16>(p, maps, dev.sm_count, s) : launch_tc_updat<64, false, __half>(p, maps, dev.sm_count, s);
+  if (f32out) return bf ? launch_tc_updat<64, true, float>(p, maps, dev.sm_grid, s) : launch_tc_updat<64, false, float>(p, maps, dev.sm_grid, s);
+  return bf ? launch_tc_updat<64, true, __nv_bfloat16>(p, maps, dev.sm_grid, s) : launch_tc_updat<64, false, __half>(p, maps, dev.sm_grid, s);
 }
 
 }  // namespace bsmm

@@ -122,8 +122,8 @@ class BlocksparseMatMul(object):
             tb = _TILE_BLOCKS.get(self.bsize)
             if tb:
                 d["xprop_sched"] = {}          # (bprop, n_tiles) -> (tensor, n_tiles, groups_off), built on demand
-                d["cta_slots"] = torch.cuda.get_device_properties(device).multi_processor_count * _OCC[self.bsize]
-                us, uoff = self._luts.updat_schedule(self.bsize, n_cta=torch.cuda.get_device_properties(device).multi_processor_count)
+                d["cta_slots"] = _lib.grid_sms(device) * _OCC[self.bsize]
+                us, uoff = self._luts.updat_schedule(self.bsize, n_cta=_lib.grid_sms(device))
                 d["updat_sched"] = torch.as_tensor(us, device=device)
                 d["updat_tiles"], d["updat_kt"] = int(us[0]), int(us[2])
             self._dev[key] = d
