@@ -23,6 +23,7 @@ SIGNATURES = {
     "bsmm_last_kernel": (_c.c_char_p, []),
     "bsmm_device_info": (_i, [_c.POINTER(_i)] * 3),
     "bsmm_device_error": (_i, []),
+    "bsmm_set_wait_timeout_ms": (_i, [_i, _i]),
     "bsmm_xprop": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bsmm_updat": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i,
                         _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
@@ -105,3 +106,37 @@ def ptr(t):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def _iter_tensors(objs):
+    import torch
+    for o in objs:
+        if torch.is_tensor(o):
+            yield o
+        elif isinstance(o, (list, tuple)):
+            for t in _iter_tensors(o):
+                yield t
+
+
+def guarded(fn):
+    """Decorator for the raw ops: every CUDA operand must live on ONE device, and the call runs with that device
+    current -- kernels launch on torch's current stream of the current device, and device properties, grid sizes and
+    the tensor-map context come from cudaGetDevice, so an op on cuda:1 tensors while cuda:0 is current would otherwise
+    launch on the wrong GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        import torch
+        dev = None
+        for t in _iter_tensors(list(args) + list(kw.values())):
+            if t.is_cuda:
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise ValueError("%s: operands live on different devices (%s and %s)" % (fn.__name__, dev, t.device))
+        if dev is None or torch.cuda.current_device() == dev.index:
+            return fn(self, *args, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kw)
+    return wrapper

@@ -28,7 +28,20 @@ int bsmm_device_error(void) {
   if (e != cudaSuccess) { cudaGetLastError(); fail((int)e, "device fault: %s", cudaGetErrorString(e)); return -1; }
   if (cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int)) != cudaSuccess) return -1;
   if (v != 0) cudaMemcpyToSymbol(g_tc_error, &zero, sizeof(int));
-  return v;
+  int wv = 0;
+  if (cudaMemcpyFromSymbol(&wv, ptx::g_wait_error, sizeof(int)) != cudaSuccess) return -1;
+  if (wv != 0) cudaMemcpyToSymbol(ptx::g_wait_error, &zero, sizeof(int));
+  return v ? v : wv;
+}
+
+int bsmm_set_wait_timeout_ms(int ms, int trap) {
+  if (ms <= 0) return fail(BSMM_E_ARG, "bsmm_set_wait_timeout_ms: ms must be positive");
+  const unsigned long long ns = (unsigned long long)ms * 1000000ull;
+  const int t = trap ? 1 : 0;
+  cudaError_t e = cudaMemcpyToSymbol(ptx::g_wait_timeout_ns, &ns, sizeof(ns));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(ptx::g_wait_trap, &t, sizeof(t));
+  if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "bsmm_set_wait_timeout_ms: %s", cudaGetErrorString(e)); }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -94,4 +94,18 @@ inline const DeviceInfo& device_info() {
   return info;
 }
 
+// cudaFuncSetAttribute is per device: `mask` (one static per kernel instantiation) remembers the device ordinals a
+// kernel has already been configured on, so a host thread that moves between GPUs configures each of them once.
+template <typename K>
+inline int ensure_dyn_smem(K kern, size_t smem, uint64_t& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(BSMM_E_NODEV, "no CUDA device");
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask & bit) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+  mask |= bit;
+  return 0;
+}
+
 }  // namespace bsmm

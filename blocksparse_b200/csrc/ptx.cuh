@@ -50,8 +50,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: returns false if the barrier did not flip within ~2 s of wall clock, so that a
-// protocol bug surfaces as an error instead of hanging the GPU.
+// Bounded wait: a barrier that does not flip within g_wait_timeout_ns of wall clock (default 2 s, host-settable
+// through bsmm_set_wait_timeout_ms) is a protocol bug or a starved kernel.  The first wait that gives up records
+// code 100 in g_wait_error and -- unless trapping is disabled (probes, tests of the error path) -- executes
+// `trap`, so that the launch FAILS (the next CUDA call of the host returns a fault) instead of completing with
+// partially written outputs.
+__device__ unsigned long long g_wait_timeout_ns = 2000000000ull;
+__device__ int g_wait_trap = 1;
+__device__ int g_wait_error = 0;
+__device__ __noinline__ void wait_timed_out() {
+  g_wait_error = 100;
+  __threadfence_system();
+  if (g_wait_trap) asm volatile("trap;");
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -67,8 +78,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     for (int i = 0; i < 64; ++i)
       if (mbar_try_wait(bar, parity)) return true;
     if (abort_flag && *abort_flag) return false;
-    if (globaltimer_ns() - t0 > 500000000ull) {
+    if (globaltimer_ns() - t0 > g_wait_timeout_ns) {
       if (abort_flag) *abort_flag = 1;
+      wait_timed_out();
       return false;
     }
   }
@@ -101,8 +113,9 @@ __device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, volat
     for (int i = 0; i < 64; ++i)
       if (mbar_try_wait_a(bar, parity)) return true;
     if (abort_flag && *abort_flag) return false;
-    if (globaltimer_ns() - t0 > 500000000ull) {
+    if (globaltimer_ns() - t0 > g_wait_timeout_ns) {
       if (abort_flag) *abort_flag = 1;
+      wait_timed_out();
       return false;
     }
   }

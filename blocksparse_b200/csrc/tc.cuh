@@ -452,12 +452,8 @@ template <int BS, bool BF16, int OCC, int VAR = 0>
 int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count, cudaStream_t s) {
   auto kern = tc_xprop_kernel<BS, BF16, OCC, VAR>;
   constexpr size_t smem = xprop_smem_bytes<BS, OCC, VAR>();
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static thread_local uint64_t configured = 0;
+  if (int e = ensure_dyn_smem(kern, smem, configured)) return e;
   const int total = p.n_ktiles * p.n_ntiles;
   const int grid = total < sm_count * OCC ? total : sm_count * OCC;
   kern<<<grid, xprop_threads<XpropCfg<BS, OCC, VAR>>(), smem, s>>>(p, maps);

@@ -416,8 +416,8 @@ inline int tc_bst_nt(int dtype, int c_dtype, int bsize, const int32_t* items, in
   const bool bf = dtype == BSMM_BF16;
 #define BSMM_LAUNCH_NT(BFV, TCV)                                                         \
   { auto kern = tc_bst_nt_kernel<BFV, TCV>;                                              \
-    static thread_local bool cfg = false;                                                \
-    if (!cfg) { if (int e = bst_set_smem(kern, smem)) return e; cfg = true; }            \
+    static thread_local uint64_t cfg = 0;                                                \
+    if (int e = ensure_dyn_smem(kern, smem, cfg)) return e;                              \
     kern<<<grid, BST_THREADS, smem, s>>>(p, maps); }
   if (c_dtype == BSMM_F32) { if (bf) BSMM_LAUNCH_NT(true, float) else BSMM_LAUNCH_NT(false, float) }
   else if (c_dtype == BSMM_BF16) { if (bf) BSMM_LAUNCH_NT(true, __nv_bfloat16) else BSMM_LAUNCH_NT(false, __nv_bfloat16) }
@@ -447,13 +447,13 @@ inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const i
   const int grid = (int)(total < sm ? total : sm);
   if (dtype == BSMM_BF16) {
     auto kern = tc_bst_xn_kernel<true>;
-    static thread_local bool cfg = false;
-    if (!cfg) { if (int e = bst_set_smem(kern, smem)) return e; cfg = true; }
+    static thread_local uint64_t cfg = 0;
+    if (int e = ensure_dyn_smem(kern, smem, cfg)) return e;
     kern<<<grid, BST_THREADS, smem, s>>>(p, maps);
   } else {
     auto kern = tc_bst_xn_kernel<false>;
-    static thread_local bool cfg = false;
-    if (!cfg) { if (int e = bst_set_smem(kern, smem)) return e; cfg = true; }
+    static thread_local uint64_t cfg = 0;
+    if (int e = ensure_dyn_smem(kern, smem, cfg)) return e;
     kern<<<grid, BST_THREADS, smem, s>>>(p, maps);
   }
   return check_launch(transpose_a ? "tcgen05_bst_tn" : "tcgen05_bst_nn");

@@ -233,12 +233,8 @@ template <int BS, bool BF16, typename TO>
 int launch_tc_updat(const UpdatTcParams& p, const UpdatTmaps& maps, int sm_count, cudaStream_t s) {
   auto kern = tc_updat_kernel<BS, BF16, TO>;
   constexpr size_t smem = updat_smem_bytes<BS>();
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static thread_local uint64_t configured = 0;
+  if (int e = ensure_dyn_smem(kern, smem, configured)) return e;
   const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
   kern<<<grid, UPDAT_THREADS, smem, s>>>(p, maps);
   return check_launch(BS == 32 ? "tcgen05_updat_bs32" : "tcgen05_updat_bs64");

@@ -22,6 +22,7 @@ _OCC = {32: 2, 64: 1} if _OCC_ENV not in ("1", "2") else {32: int(_OCC_ENV), 64:
 _WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))     # tuning aid: force the W-slots-per-stage variant (2 or 4)
 _TILE_BLOCKS = {bs: (256 if occ == 2 else 512) // bs for bs, occ in _OCC.items()}
 # W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
+_SCHED_CACHE_MAX = 16
 _W_PER_GROUP = {32: 8, 64: 2 if _OCC[64] == 2 else 4}
 
 
@@ -99,15 +100,20 @@ class BlocksparseMatMul(object):
         return torch.as_tensor(((cs & 1) ^ (ks & 1) ^ 1).astype(np.float32), device=device).to(dtype)
 
     def prune(self, param, gate):
-        """Drop blocks whose gate is zero (matmul.py:272-291); returns (new_param, new_gate, new_layout)."""
+        """Drop blocks whose gate is zero (matmul.py:272-291).
+
+        Like the reference, returns (new_param, new_gate) and clears the pruned blocks in `self.layout` in place; the
+        LUTs of this object are NOT rebuilt -- construct a new BlocksparseMatMul from `self.layout` for the pruned op.
+        """
         gate_np = gate.detach().cpu().numpy() if torch.is_tensor(gate) else np.asarray(gate)
         keep = gate_np != 0.0
-        layout = self.layout.copy()
         for w in np.nonzero(~keep)[0]:
             c, k = self.updat_list[w]
-            layout[c, k] = False
+            self.layout[c, k] = False
         idx = torch.as_tensor(np.nonzero(keep)[0], device=param.device)
-        return param.index_select(0, idx), torch.ones(int(keep.sum()), dtype=gate.dtype, device=param.device), layout
+        new_gate = torch.ones(int(keep.sum()), dtype=gate.dtype if torch.is_tensor(gate) else torch.float32,
+                              device=param.device)
+        return param.index_select(0, idx), new_gate
 
     # ------------------------------------------------------------------ device state
     def _device_luts(self, device):
@@ -136,6 +142,7 @@ class BlocksparseMatMul(object):
     def bprop(self, dy, w, gate=None, flags=0):
         return self._xprop(dy, w, True, gate, flags)
 
+    @_lib.guarded
     def _xprop(self, x, w, bprop, gate, flags):
         lib = _lib.load()
         if not x.is_cuda:
@@ -169,6 +176,8 @@ class BlocksparseMatMul(object):
             key = (bool(bprop), n_kt, wpg)
             if key not in d["xprop_sched"]:
                 arr, off = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt)
+                while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:       # bounded: one entry per distinct tile count
+                    d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
                 d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off)
             sched, sched_tiles, sched_off = d["xprop_sched"][key]
             tile_arg = tb | ((wpg << 8) if sparse else 0)
@@ -193,6 +202,7 @@ class BlocksparseMatMul(object):
             return y2.reshape((feat_out,) + tuple(x.shape[1:]))
         return y2.reshape(tuple(x.shape[:-1]) + (feat_out,))
 
+    @_lib.guarded
     def updat(self, xs, dys, dw=None, alpha=1.0, gate=None, dw_gated=False, dw_dtype=None, flags=0):
         """DW[w] = alpha * sum_p X_p . DY_p^T (+ dw if given: in-place accumulate, DWA semantics)."""
         lib = _lib.load()
@@ -234,6 +244,7 @@ class BlocksparseMatMul(object):
         _lib.check(rc, "bsmm_updat")
         return dw
 
+    @_lib.guarded
     def gate_grad(self, dw, w):
         """dg[w] = sum(dw[w] * w[w])  (BlocksparseMatmulDG, matmul.py:519-523)."""
         lib = _lib.load()
@@ -359,6 +370,10 @@ class group_param_grads(object):
 
     def __init__(self, bsmm, w, group_size=8):
         assert 1 <= group_size <= _lib.MAX_PAIRS
+        if not w.is_leaf:
+            # the total is written to w.grad on exit: a derived tensor (a cast, a view of a fused parameter) would
+            # swallow it, and its data_ptr would not match the tensor the op sees
+            raise ValueError("group_param_grads needs the leaf parameter that is passed to the op, got a derived tensor")
         self.key = (id(bsmm), w.data_ptr())
         self.pending = _Pending(bsmm, w, group_size)
         self.w = w
@@ -371,6 +386,9 @@ class group_param_grads(object):
         _groups.pop(self.key, None)
         if exc[0] is None:
             self.pending.flush()
+            if self.pending.launches == 0:
+                raise RuntimeError("group_param_grads: no backward use of this (op, parameter) pair was seen inside the "
+                                   "block -- was the op called with a cast or a view of the parameter?")
             if self.pending.dw is not None:
                 g = self.pending.dw.to(self.w.dtype)
                 self.w.grad = g if self.w.grad is None else self.w.grad + g

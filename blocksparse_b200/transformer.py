@@ -72,6 +72,7 @@ class BlocksparseTransformer(object):
         return d
 
     # ------------------------------------------------------------------ raw ops
+    @_lib.guarded
     def _nt(self, a, b, c_dtype, flags=0):
         lib = _lib.load()
         if not a.is_cuda:
@@ -93,6 +94,7 @@ class BlocksparseTransformer(object):
         _lib.check(rc, "bst_nt")
         return c
 
+    @_lib.guarded
     def _xn(self, a, b, transpose_a, flags=0):
         lib = _lib.load()
         if not a.is_cuda:
@@ -117,6 +119,7 @@ class BlocksparseTransformer(object):
         _lib.check(rc, "bst_xn")
         return c
 
+    @_lib.guarded
     def _softmax(self, x, scale, use_mask, autoregress_at_key, dtype):
         lib = _lib.load()
         x = x.contiguous()
@@ -133,6 +136,7 @@ class BlocksparseTransformer(object):
         _lib.check(rc, "bst_softmax")
         return y
 
+    @_lib.guarded
     def _softmax_grad(self, dy, y, scale):
         lib = _lib.load()
         dy = dy.to(y.dtype).contiguous()
@@ -154,11 +158,15 @@ class BlocksparseTransformer(object):
         if self.softmax_mask_np is None:
             raise ValueError("autoregress_at_key only applies to ops with mask_callback defined.")
         lib = _lib.load()
-        d = self._device_luts(torch.device(device))
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        d = self._device_luts(device)
         out = torch.empty_like(d["mask"])
-        rc = lib.bst_autoregressive_mask(self.blk_size, d["nt"].data_ptr(), self.lut_heads, self.blocks,
-                                         d["mask"].data_ptr(), out.data_ptr(), int(autoregress_at_key),
-                                         _lib.stream_ptr())
+        with torch.cuda.device(device):        # launch on the device (and its current stream) that holds the mask
+            rc = lib.bst_autoregressive_mask(self.blk_size, d["nt"].data_ptr(), self.lut_heads, self.blocks,
+                                             d["mask"].data_ptr(), out.data_ptr(), int(autoregress_at_key),
+                                             _lib.stream_ptr())
         _lib.check(rc, "bst_autoregressive_mask")
         return out
 

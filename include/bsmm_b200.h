@@ -77,6 +77,11 @@ const char* bsmm_last_kernel(void);
 /* Debug aid: synchronises the current device, then returns and clears the sticky device-side error
  * word (non-zero if a tensor-core kernel's bounded barrier wait timed out since the last call). */
 int         bsmm_device_error(void);
+/* Every mbarrier wait inside the tcgen05 kernels is wall-clock bounded.  A wait that exceeds `ms` milliseconds
+ * (default 2000) records an error code and, when `trap` is non-zero (default), executes `trap`: the launch fails and
+ * the next CUDA call of the host reports the fault, so a starved or mis-sequenced kernel can never return partially
+ * written outputs with rc 0.  trap = 0 keeps the context alive (the kernel exits early; poll bsmm_device_error()). */
+int         bsmm_set_wait_timeout_ms(int ms, int trap);
 
 /* ---- block-sparse matmul -------------------------------------------------------- */
 

@@ -37,14 +37,22 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void
       : "memory");
 }
 
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* src, uint64_t* bar, uint32_t bytes) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(ptx::smem_u32(bar)) : "memory");
+}
+
 struct Params {
+  const uint8_t* src;
   int box_bytes;        // bytes per TMA box
   int boxes_per_stage;  // boxes landing on one barrier
   int stages;           // ring depth
   int iters;            // stages filled per CTA
   int n_boxes;          // distinct boxes in the source (walk is strided so CTAs do not share lines)
   int rows_per_box;     // outer extent of a box (coordinate step)
-  int multicast;        // 0 = every CTA loads its own tile; 1 = cluster of 2, each CTA loads half and multicasts it
+  int multicast;        // 0 = every CTA loads its own tile; 1 = cluster, each CTA loads 1/G of the stage and multicasts it; 2 = cluster, every CTA loads everything (same tiles)
+  int G;                // cluster size
+  int bulk1d;           // 1 = plain cp.async.bulk of box_bytes contiguous bytes instead of a tensor-map box
 };
 
 // free-running ring: lane 0 of warp 0 keeps `stages` stages in flight
@@ -65,7 +73,7 @@ __global__ void __launch_bounds__(32) ingest_kernel(const __grid_constant__ CUte
   const long long t0 = clock64();
   if (lane == 0) {
     // the tile a CTA (or a cluster) pulls at step i: a different box every time, spread over the whole source
-    const unsigned base = (p.multicast ? blockIdx.x / 2 : blockIdx.x) * 7919u;
+    const unsigned base = (p.multicast ? blockIdx.x / p.G : blockIdx.x) * 7919u;
     auto issue = [&](int i) {
       const int st = i % p.stages;
       uint8_t* dst = smem + st * stage_bytes;
@@ -73,13 +81,14 @@ __global__ void __launch_bounds__(32) ingest_kernel(const __grid_constant__ CUte
       if (!p.multicast) {
         for (int b = 0; b < p.boxes_per_stage; ++b) {
           const unsigned box = (base + (unsigned)(i * p.boxes_per_stage + b) * 13u) % (unsigned)p.n_boxes;
-          ptx::tma_load_2d(dst + b * p.box_bytes, &map, &full[st], 0, (int)box * p.rows_per_box);
+          if (p.bulk1d) bulk_load_1d(dst + b * p.box_bytes, p.src + (size_t)box * p.box_bytes, &full[st], p.box_bytes);
+          else ptx::tma_load_2d(dst + b * p.box_bytes, &map, &full[st], 0, (int)box * p.rows_per_box);
         }
       } else {
         // each CTA fetches every other box of the stage and delivers it to both CTAs
-        for (int b = (int)rank; b < p.boxes_per_stage; b += 2) {
+        for (int b = (int)rank; b < p.boxes_per_stage; b += p.G) {
           const unsigned box = (base + (unsigned)(i * p.boxes_per_stage + b) * 13u) % (unsigned)p.n_boxes;
-          tma_load_2d_multicast(dst + b * p.box_bytes, &map, &full[st], 0, (int)box * p.rows_per_box, (uint16_t)3);
+          tma_load_2d_multicast(dst + b * p.box_bytes, &map, &full[st], 0, (int)box * p.rows_per_box, (uint16_t)((1u << p.G) - 1));
         }
       }
     };
@@ -104,10 +113,10 @@ __global__ void __launch_bounds__(32) ingest_kernel(const __grid_constant__ CUte
         for (int s = 0; s < p.stages; ++s) {
           uint8_t* dst = smem + s * stage_bytes;
           ptx::mbar_expect_tx(&full[s], stage_bytes);
-          const unsigned base = (blockIdx.x / 2) * 7919u;
-          for (int b = (p.multicast == 1 ? (int)rank : 0); b < p.boxes_per_stage; b += (p.multicast == 1 ? 2 : 1)) {
+          const unsigned base = (blockIdx.x / p.G) * 7919u;
+          for (int b = (p.multicast == 1 ? (int)rank : 0); b < p.boxes_per_stage; b += (p.multicast == 1 ? p.G : 1)) {
             const unsigned box = (base + (unsigned)((r0 + s) * p.boxes_per_stage + b) * 13u) % (unsigned)p.n_boxes;
-            if (p.multicast == 1) tma_load_2d_multicast(dst + b * p.box_bytes, &map, &full[s], 0, (int)box * p.rows_per_box, (uint16_t)3);
+            if (p.multicast == 1) tma_load_2d_multicast(dst + b * p.box_bytes, &map, &full[s], 0, (int)box * p.rows_per_box, (uint16_t)((1u << p.G) - 1));
             else                  ptx::tma_load_2d(dst + b * p.box_bytes, &map, &full[s], 0, (int)box * p.rows_per_box);
           }
         }
@@ -137,7 +146,7 @@ EncodeFn get_encode() {
 struct Shape { const char* name; int inner_elems, rows; CUtensorMapSwizzle swz; };
 
 void run(EncodeFn enc, void* src, size_t src_bytes, const Shape& sh, int boxes_per_stage, int stages, int ctas_per_sm, int multicast,
-         long long* cyc, int* st, int sm_count, double clock_ghz) {
+         long long* cyc, int* st, int sm_count, double clock_ghz, int G = 2, int bulk1d = 0) {
   const int box_bytes = sh.inner_elems * 2 * sh.rows;
   // source viewed as [n_rows][row_elems]: row pitch 8 KB like the activation matrix of BASELINE cfg 2
   const uint64_t row_elems = 4096;
@@ -153,21 +162,23 @@ void run(EncodeFn enc, void* src, size_t src_bytes, const Shape& sh, int boxes_p
   Params p;
   p.box_bytes = box_bytes; p.boxes_per_stage = boxes_per_stage; p.stages = stages;
   p.iters = 4096 / boxes_per_stage / stages * stages;      // a multiple of the ring depth
-  p.rows_per_box = sh.rows; p.n_boxes = (int)(n_rows / sh.rows); p.multicast = multicast;
+  p.rows_per_box = sh.rows; p.n_boxes = (int)(n_rows / sh.rows); p.multicast = multicast; p.G = multicast ? G : 1; p.bulk1d = bulk1d;
+  p.src = (const uint8_t*)src;
+  if (bulk1d) p.n_boxes = (int)(src_bytes / box_bytes);
   const size_t smem = (size_t)box_bytes * boxes_per_stage * stages;
-  const int grid = sm_count * ctas_per_sm;
+  const int grid = multicast ? (sm_count / G) * G * ctas_per_sm : sm_count * ctas_per_sm;
   CK(cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaMemset(st, 0, 4));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = multicast ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = multicast ? G : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   for (int rep = 0; rep < 2; ++rep) {                        // first pass warms L2
     CK(cudaLaunchKernelEx(&cfg, ingest_kernel, m, p, cyc, st));
     cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("%-28s LAUNCH ERROR %s\n", sh.name, cudaGetErrorString(e)); exit(1); }
+    if (e != cudaSuccess) { printf("%-28s LAUNCH ERROR %s\n", sh.name, cudaGetErrorString(e)); return; }
   }
   std::vector<long long> h(grid);
   CK(cudaMemcpy(h.data(), cyc, grid * 8, cudaMemcpyDeviceToHost));
@@ -175,8 +186,8 @@ void run(EncodeFn enc, void* src, size_t src_bytes, const Shape& sh, int boxes_p
   long long mx = 0; for (long long v : h) mx = v > mx ? v : mx;
   const double bytes_per_cta = (double)p.iters * box_bytes * boxes_per_stage;       // bytes that land in each CTA
   const double per_sm = bytes_per_cta * ctas_per_sm / (double)mx;                    // bytes / cycle / SM
-  printf("%-28s boxes/stage %d stages %2d ctas/sm %d %-9s | %6.1f B/clk/SM  %6.2f TB/s at %.2f GHz  (%s)\n", sh.name, boxes_per_stage, stages,
-         ctas_per_sm, multicast == 1 ? "multicast" : multicast == 2 ? "rounds" : "ring", per_sm, per_sm * sm_count * clock_ghz / 1e3, clock_ghz,
+  printf("%-28s%s G%d boxes/stage %d stages %2d ctas/sm %d %-9s | %6.1f B/clk/SM  %6.2f TB/s at %.2f GHz  (%s)\n", sh.name, bulk1d ? " bulk1d" : "", p.G, boxes_per_stage, stages,
+         ctas_per_sm, multicast == 1 ? "multicast" : multicast == 2 ? "rounds" : "ring", per_sm, per_sm * grid / ctas_per_sm * clock_ghz / 1e3, clock_ghz,
          status ? "TIMEOUT" : "ok");
 }
 
@@ -205,6 +216,22 @@ int main() {
     }
     run(enc, src, src_bytes, w64, 4, 8, ctas, 0, cyc, st, sms, ghz);
     run(enc, src, src_bytes, w32, 8, 8, ctas, 0, cyc, st, sms, ghz);
+  }
+  // 1-D bulk copies of contiguous 2 KB (a W block) and 8 KB
+  const Shape b2k = {"bulk 2 KB", 32, 32, CU_TENSOR_MAP_SWIZZLE_64B};
+  const Shape b8k = {"bulk 8 KB", 32, 128, CU_TENSOR_MAP_SWIZZLE_64B};
+  const Shape x128w = {"X tile 128 x 128B (SW128)", 64, 128, CU_TENSOR_MAP_SWIZZLE_128B};   // two input blocks wide, 16 KB
+  for (int ctas : {1, 2}) {
+    run(enc, src, src_bytes, b2k, 4, 8, ctas, 0, cyc, st, sms, ghz, 1, 1);
+    run(enc, src, src_bytes, b8k, 1, 8, ctas, 0, cyc, st, sms, ghz, 1, 1);
+    run(enc, src, src_bytes, x128w, 1, 6, ctas, 0, cyc, st, sms, ghz);
+  }
+  // clusters of G CTAs pulling the SAME X tiles (8 KB boxes, 8 per stage): multicast vs everyone loads everything
+  for (int G : {2, 4, 8}) {
+    run(enc, src, src_bytes, x64, 8, 2, 1, 2, cyc, st, sms, ghz, G);
+    run(enc, src, src_bytes, x64, 8, 2, 1, 1, cyc, st, sms, ghz, G);
+    run(enc, src, src_bytes, x128, 8, 2, 1, 2, cyc, st, sms, ghz, G);
+    run(enc, src, src_bytes, x128, 8, 2, 1, 1, cyc, st, sms, ghz, G);
   }
   // cluster of two CTAs on neighbouring SMs pulling the SAME tiles: every CTA fetches half and multicasts, against
   // both CTAs fetching everything, in the same round-synchronous structure
