@@ -166,6 +166,11 @@ class MatmulLuts(object):
     def updat_schedule(self, bsize, k_per_tile=None, n_cta=None):
         return build_updat_schedule(self.updat_lut, self.CB, self.KB, bsize, k_per_tile, n_cta)
 
+    def pair_schedule(self, bprop, blocks_per_tile, w_per_group, n_tiles, n_ntiles, n_ctas, bsize=32):
+        outs, ins, wids = self._b if bprop else self._f
+        n_out = self.CB if bprop else self.KB
+        return build_pair_schedule(outs, ins, wids, n_out, blocks_per_tile, w_per_group, n_tiles, n_ntiles, n_ctas, bsize)
+
     def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None):
         outs, ins, wids = self._b if bprop else self._f
         n_out = self.CB if bprop else self.KB
@@ -296,6 +301,137 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     gr[run_group, 12 + run_pos] = r0
     gr[run_group, 20 + run_pos] = r1
     return sched, grp_off
+
+
+PAIR_MAX_W = 14          # W blocks per pair-group record (ints 2..15)
+PAIR_MAX_RUNS = 8        # MMA runs per half of a pair-group (ints 16..23 / 24..31)
+
+
+def lpt_tile_lists(tile_cost, n_ntiles, n_ctas):
+    """Static longest-processing-time assignment of the n_ntiles x len(tile_cost) tiles to n_ctas persistent CTAs.
+
+    The persistent grids used to deal tile t to CTA t mod grid; with skewed layouts (a few output tiles hold most of
+    the blocks) that leaves CTAs idle while one works through several heavy tiles.  Here tiles are sorted by
+    decreasing cost and each goes to the least-loaded CTA so far (ties: lowest CTA index => deterministic).
+    Returns int32 [n_ctas + 1 offsets | tile ids], tile id = n_tile * n_ktiles + k_tile.
+    """
+    import heapq
+    n_kt = len(tile_cost)
+    cost = np.asarray(tile_cost, dtype=np.float64)
+    kt = np.tile(np.arange(n_kt), n_ntiles)
+    nt = np.repeat(np.arange(n_ntiles), n_kt)
+    order = np.lexsort((nt, kt, -cost[kt]))                 # heaviest first; stable in (kt, nt)
+    heap = [(0.0, c) for c in range(n_ctas)]
+    lists = [[] for _ in range(n_ctas)]
+    for i in order.tolist():
+        load, c = heapq.heappop(heap)
+        lists[c].append(int(nt[i]) * n_kt + int(kt[i]))
+        heapq.heappush(heap, (load + float(cost[kt[i]]), c))
+    offs = np.concatenate(([0], np.cumsum([len(l) for l in lists]))).astype(np.int32)
+    flat = np.asarray([t for l in lists for t in l], dtype=np.int32)
+    return np.concatenate((offs, flat)).astype(np.int32)
+
+
+def build_pair_schedule(outs, ins, wids, n_out, blocks_per_tile, w_per_group, n_tiles, n_ntiles, n_ctas, bsize=32):
+    """Schedule for the wide-activation-tile tcgen05 xprop kernel (csrc/tc_xprop2.cuh, 32 x 32 blocks).
+
+    Same idea as build_tile_schedule, but a group is an input-block PAIR (2p, 2p+1): its activation tile is
+    128 rows x 64 features = 128-byte rows, so every TMA row request moves a full 128-byte line (the 64-byte rows of
+    the single-block tile left the SM's L1->crossbar request port -- one request per cycle -- 67 % busy at 45 B/clk,
+    profiles/r1_ncu_tc_kernels.txt), and ~2x the W blocks consume each staged tile.  W blocks are listed half 0
+    (input block 2p) first, then half 1, each in accumulator order, so that the runs of one half are issued back to
+    back against the same K slices of the tile (A-collector reuse).
+
+    int32 layout:
+      [0] n_tiles  [1] blocks_per_tile  [2] total groups  [3] total W loads
+      tile header   [n_tiles][4] = (first_group_index, n_groups, first_out_block, n_out | touched_mask << 8)
+      (padding to a multiple of GROUP_INTS ints)
+      group records [groups][32]:
+          [0] input pair p   [1] n_w | n_runs_half0 << 8 | n_runs_half1 << 16
+          [2..15]   W block ids in staging-slot order
+          [16..23]  runs of half 0, [24..31] runs of half 1, one packed int each:
+                    (staging slot * bsize*bsize*2) >> 4  |  accumulator column << 12  |  (N >> 3) << 21
+      tile lists    lpt_tile_lists(...) for n_ntiles minibatch tiles on n_ctas CTAs
+    Returns (schedule, groups_offset, tile_list_offset).
+    """
+    T = int(blocks_per_tile)
+    WPS = int(w_per_group)
+    assert 1 <= WPS <= PAIR_MAX_W and T * bsize <= 512
+    n_tiles = int(n_tiles)
+    assert n_tiles * T >= n_out
+    bounds = (np.arange(n_tiles + 1, dtype=np.int64) * n_out) // n_tiles
+    assert int(np.diff(bounds).max()) <= T
+    outs = np.asarray(outs, dtype=np.int64)
+    ins = np.asarray(ins, dtype=np.int64)
+    wids = np.asarray(wids, dtype=np.int64)
+    nnz = len(outs)
+    tile = np.searchsorted(bounds, outs, side="right") - 1
+    pair, half = ins >> 1, ins & 1
+    slot = outs - bounds[tile]
+    order = np.lexsort((slot, half, pair, tile))
+    tile_s, pair_s, half_s, slot_s, w_s = tile[order], pair[order], half[order], slot[order], wids[order]
+    new_cluster = np.ones(nnz, dtype=bool)
+    if nnz:
+        new_cluster[1:] = (tile_s[1:] != tile_s[:-1]) | (pair_s[1:] != pair_s[:-1])
+    c_start = np.nonzero(new_cluster)[0].tolist() + [nnz]
+    max_run = 256 // bsize
+    wbytes16 = (bsize * bsize * 2) >> 4
+    half_l, slot_l, w_l = half_s.tolist(), slot_s.tolist(), w_s.tolist()
+    recs, rec_tile = [], []
+    for ci in range(len(c_start) - 1):
+        a, b = c_start[ci], c_start[ci + 1]
+        t, p = int(tile_s[a]), int(pair_s[a])
+        i = a
+        while i < b:
+            rec = [0] * GROUP_INTS
+            runs = ([], [])
+            j, prev = i, None
+            while j < b and j - i < WPS:
+                h, sl = half_l[j], slot_l[j]
+                cont = prev == (h, sl - 1) and runs[h][-1][2] < max_run
+                if not cont:
+                    if len(runs[h]) == PAIR_MAX_RUNS:
+                        break
+                    runs[h].append([j - i, sl, 1])
+                else:
+                    runs[h][-1][2] += 1
+                rec[2 + j - i] = w_l[j]
+                prev = (h, sl)
+                j += 1
+            rec[0] = p
+            rec[1] = (j - i) | (len(runs[0]) << 8) | (len(runs[1]) << 16)
+            for h in (0, 1):
+                for r, (pos, sl, ln) in enumerate(runs[h]):
+                    rec[16 + 8 * h + r] = (pos * wbytes16) | ((sl * bsize) << 12) | (((ln * bsize) >> 3) << 21)
+            recs.append(rec)
+            rec_tile.append(t)
+            i = j
+    n_groups = len(recs)
+    rec_tile = np.asarray(rec_tile, dtype=np.int64)
+    groups_per_tile = np.bincount(rec_tile, minlength=n_tiles) if n_groups else np.zeros(n_tiles, dtype=np.int64)
+    tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
+    w_per_tile = np.bincount(tile, minlength=n_tiles) if nnz else np.zeros(n_tiles, dtype=np.int64)
+    touched = np.zeros(n_tiles, dtype=np.int64)
+    np.bitwise_or.at(touched, tile, np.int64(1) << (outs - bounds[tile]))
+
+    hdr_ints = 4 + 4 * n_tiles
+    grp_off = ceil_div(hdr_ints, GROUP_INTS) * GROUP_INTS
+    # cost model of a tile in L1->crossbar requests / tensor-pipe cycles: 128 row requests per activation tile,
+    # 32 per W block (~ its 32+ MMA cycles), plus the epilogue
+    cost = 128.0 * groups_per_tile + 40.0 * w_per_tile + 10.0 * T * bsize / 8 + 200.0
+    lists = lpt_tile_lists(cost, int(n_ntiles), int(n_ctas))
+    list_off = grp_off + GROUP_INTS * n_groups
+    sched = np.zeros(list_off + len(lists), dtype=np.int32)
+    sched[0:4] = (n_tiles, T, n_groups, nnz)
+    th = sched[4:hdr_ints].reshape(n_tiles, 4)
+    th[:, 0] = tile_first_group
+    th[:, 1] = groups_per_tile
+    th[:, 2] = bounds[:-1]
+    th[:, 3] = np.diff(bounds) | (touched << 8)
+    if n_groups:
+        sched[grp_off:list_off] = np.asarray(recs, dtype=np.int64).astype(np.int32).reshape(-1)
+    sched[list_off:] = lists
+    return sched, grp_off, list_off
 
 
 UPDAT_REC_INTS = 64      # one 256-byte record per updat tile

@@ -230,6 +230,25 @@ class MatmulOracle(object):
                 U[w] = Iv[c] @ Ev[k].T
         return U
 
+    def updat_blocks(self, I, E, block_ids):
+        """matmul.py:401-419 restricted to the listed block ids (full-size checks sample the blocks: the loop body
+        is the reference's `U[w] = dot(I[c], E[k].T)` line unchanged)."""
+        bs = self.bsize
+        U = np.zeros((len(block_ids), bs, bs))
+        if self.axis:
+            Iv = I.reshape(-1, self.CB, bs)
+            Ev = E.reshape(-1, self.KB, bs)
+            for i, w in enumerate(block_ids):
+                c, k = self.updat_list[w]
+                U[i] = Iv[:, c, :].astype(np.float64).T @ Ev[:, k, :].astype(np.float64)
+            return U
+        Iv = I.reshape(self.CB, bs, -1)
+        Ev = E.reshape(self.KB, bs, -1)
+        for i, w in enumerate(block_ids):
+            c, k = self.updat_list[w]
+            U[i] = Iv[c].astype(np.float64) @ Ev[k].astype(np.float64).T
+        return U
+
     # ---- dense cross-check ("NumPy einsum reference of the same layout") ----
 
     def dense_weight(self, W):
