@@ -10,7 +10,15 @@ density 25 % unless --density is given).  Metric = effective TFLOP/s
 
 N>1 is launched by torchrun (one rank per GPU): the minibatch axis is sharded (weak
 scaling: every rank holds N=4096 columns), fprop/bprop need no communication and the
-updat output dW is all-reduced with NCCL.
+updat output dW (fp32 when N>1) is all-reduced with NCCL on a side stream, overlapping the
+next step's fprop/bprop, with BSMM_SM_MARGIN SMs left free for the NCCL kernel.
+
+Besides the headline the JSON line carries (rank 0, skipped with --no-extras):
+  check           max_rel_err / l2_err of Y, DX, DW taken from the TIMED buffers against the oracle (row/block sample)
+  density_sweep   every op at 5/10/25/50/100 % density with frac_tensor_peak and frac_hbm_peak, cold and warm L2
+  variants        the skewed Barabasi-Albert layout, feature_axis 0, block size 64, fp16 at the headline density
+  cfg3 / cfg4     the block-sparse attention ops and the block-size sweep of BASELINE configs[2] / [3]
+  cfg5_strong     BASELINE configs[4]: global N=32768 split over the ranks (strong scaling), per-rank N = 32768/world
 """
 import argparse
 import json
@@ -204,6 +212,67 @@ def cpu_reference(density, axis, budget_s=20.0, steps=1):
             "ms_per_sample": dt * 1e3}, dt
 
 
+def time_loop(torch, fn, reps, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(reps):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def op_record(ms, flops, nbytes, pk, kernel=None):
+    r = {"ms": ms, "tflops": flops / (ms * 1e-3) / 1e12, "frac_tensor_peak": flops / (ms * 1e-3) / 1e12 / pk["tf_burst"],
+         "hbm_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
+    if kernel:
+        r["kernel"] = kernel
+    return r
+
+
+def time_three_ops(torch, _lib, bsmm, W, Xs, Es, pk, reps=20, warm_l2=False):
+    """fprop / bprop / updat of one BlocksparseMatMul, each alone.  cold: rotating input sets (> L2); warm: same buffers."""
+    n = len(Xs)
+    N = Xs[0].numel() // bsmm.C
+    fl = 2.0 * bsmm.blocks * bsmm.bsize ** 2 * N
+    by = 2.0 * (bsmm.C * N + bsmm.K * N) + 2.0 * bsmm.blocks * bsmm.bsize ** 2
+    out = {}
+    pick = (lambda i: 0) if warm_l2 else (lambda i: i % n)
+    for name, fn in [("fprop", lambda i: bsmm.fprop(Xs[pick(i)], W)), ("bprop", lambda i: bsmm.bprop(Es[pick(i)], W)),
+                     ("updat", lambda i: bsmm.updat([Xs[pick(i)]], [Es[pick(i)]]))]:
+        ms = time_loop(torch, fn, reps)
+        out[name] = op_record(ms, fl, by, pk, _lib.last_kernel())
+    return out
+
+
+def check_against_oracle(torch, bsmm, lay, axis, W, X, E, y, dx, dw, n_rows=32, n_blocks=64):
+    """Sample of the step's own outputs against the oracle (bounded CPU work, test infrastructure used as the checker)."""
+    from oracle.bsmm_oracle import MatmulOracle
+    orc = MatmulOracle(lay, bsmm.bsize, axis)
+    N = X.shape[0] if axis else X.shape[1]
+    rows = torch.as_tensor((np.arange(n_rows) * (N // n_rows) + np.arange(n_rows) % 5) % N, device=X.device)
+
+    def sample(t):
+        return (t.index_select(0, rows) if axis else t.index_select(1, rows)).float().cpu().numpy()
+
+    def errs(got, ref):
+        d = np.abs(np.asarray(got, dtype=np.float64) - ref)
+        return {"max_rel_err": float(d.max() / np.abs(ref).mean()), "l2_err": float(np.sqrt((d * d).sum() / (ref * ref).sum()))}
+
+    Wh = W.float().cpu().numpy()
+    rng = np.random.default_rng(0)
+    blk = np.sort(rng.choice(bsmm.blocks, size=min(n_blocks, bsmm.blocks), replace=False))
+    ref_dw = orc.updat_blocks(X.float().cpu().numpy(), E.float().cpu().numpy(), blk)
+    return {"fprop": errs(sample(y), orc.fprop(sample(X), Wh)), "bprop": errs(sample(dx), orc.bprop(sample(E), Wh)),
+            "updat": errs(dw.index_select(0, torch.as_tensor(blk, device=dw.device)).float().cpu().numpy(), ref_dw),
+            "sample": "%d minibatch rows (all features) for fprop/bprop, %d weight blocks (full minibatch) for updat; "
+                      "oracle = NumPy restatement of matmul.py:353-419" % (n_rows, len(blk)),
+            "tolerance": "l2_err <= 1e-2 (bf16)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -212,8 +281,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--density", type=float, default=0.25)
     ap.add_argument("--axis", type=int, default=1)
-    ap.add_argument("--sweep", action="store_true", help="also time each op at 5/10/25/50/100 %% density")
+    ap.add_argument("--sweep", action="store_true", help="(kept for compatibility: the sweep is on by default)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no sweep / variants / cfg3 / cfg4 / cfg5 sub-records")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sm-margin", type=int, default=None, help="SMs left free for NCCL when N>1 (default 8; BSMM_SM_MARGIN wins)")
+    ap.add_argument("--blocking-allreduce", action="store_true", help="round-1 behaviour: all-reduce on the compute stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,10 +310,13 @@ def main():
         print(json.dumps(line))
         return
 
+    from blocksparse_b200 import dist as bdist
+    margin = 0
+    if world > 1 and not args.blocking_allreduce:
+        margin = bdist.reserve_sms_for_nccl(8 if args.sm_margin is None else args.sm_margin)
     import torch
     import torch.distributed as dist
     from blocksparse_b200 import BlocksparseMatMul, _lib
-    from blocksparse_b200 import dist as bdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -257,26 +332,59 @@ def main():
     Xs = [(torch.randn(bsmm.i_shape(N), generator=gen, device=dev) * 0.1).to(dtype) for _ in range(NSETS)]
     Es = [(torch.randn(bsmm.o_shape(N), generator=gen, device=dev) * 0.1).to(dtype) for _ in range(NSETS)]
     launches = [0]
+    # N>1: the partial dW is produced in fp32 and summed in fp32 (8 bf16 partial sums would each be rounded to 8 bits of
+    # mantissa); the reduction runs on a side stream and overlaps the next step's fprop/bprop (the reference's
+    # AllreduceNccl pattern, src/nccl_op.cc:168,513), ordered before the next updat.
+    dw_dtype = torch.float32 if world > 1 else None
+    side = bdist.AllreduceStream(dev) if (world > 1 and not args.blocking_allreduce) else None
+    config["dw_dtype"] = "fp32" if world > 1 else "bf16"
+    config["allreduce"] = ("none (1 GPU)" if world == 1 else "blocking on the compute stream" if side is None else
+                           "side stream, overlaps the next step's fprop/bprop; %d SMs left to NCCL (NCCL_MAX_CTAS=%s)"
+                           % (margin, os.environ.get("NCCL_MAX_CTAS")))
 
-    def step(i):
-        x, e = Xs[i % NSETS], Es[i % NSETS]
-        y = bsmm.fprop(x, W)
-        dx = bsmm.bprop(e, W)
-        dw = bsmm.updat([x], [e])
-        launches[0] += 3
-        # dW all-reduce (no-op at world size 1).  Issued on the side stream or with async_op it takes the same ~47 us per
-        # step at N=2 (tools/diag_dist.py, profiles/r1_dist_diag.txt): the persistent kernels occupy every SM, so the NCCL
-        # kernel runs between them either way.
-        bdist.allreduce_dw(dw)
-        return y, dx, dw
+    def make_step(op, w, xs, es):
+        def step(i):
+            x, e = xs[i % len(xs)], es[i % len(es)]
+            y = op.fprop(x, w)
+            dx = op.bprop(e, w)
+            if side is not None:
+                side.wait()                       # the previous step's reduction is ordered before this updat
+            dw = op.updat([x], [e], dw_dtype=dw_dtype)
+            launches[0] += 3
+            if side is not None:
+                side.reduce(dw)
+            else:
+                bdist.allreduce_dw(dw)            # no-op at world size 1
+            return y, dx, dw
+        return step
+
+    step = make_step(bsmm, W, Xs, Es)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(step_fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        last = None
+        for i in range(steps):
+            last = step_fn(i)
+        if side is not None:
+            side.wait()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, last
+
     for i in range(args.warmup):
         step(i)
+    if side is not None:
+        side.wait()
     kernels = {}
     bsmm.fprop(Xs[0], W); kernels["fprop"] = _lib.last_kernel()
     bsmm.bprop(Es[0], W); kernels["bprop"] = _lib.last_kernel()
@@ -286,41 +394,27 @@ def main():
     if sampler:
         sampler.start()
     launches[0] = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        step(i)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms_per_step, last = timed(step, args.steps)
     timed_samples = len(sampler.rows) if sampler else 0
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / args.steps
+    n_launches = launches[0]
     flops_step_gpu = 3 * 2.0 * bsmm.blocks * BS * BS * N
     value = flops_step_gpu * world / (ms_per_step * 1e-3) / 1e12
 
-    # ---- per-kernel timing (each kernel alone, rotating inputs) for the roofline object
-    def time_op(fn, reps=50):
-        for i in range(3):
-            fn(i)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(reps):
-            fn(i)
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
+    # ---- correctness of what was just timed: the last step's outputs against the oracle (rank 0)
+    check = None
+    if rank == 0:
+        li = (args.steps - 1) % NSETS
+        y_l, dx_l, dw_l = last
+        if world > 1:           # the all-reduced dW is the sum over ranks: check this rank's partial instead
+            dw_l = bsmm.updat([Xs[li]], [Es[li]], dw_dtype=dw_dtype)
+        check = check_against_oracle(torch, bsmm, lay, args.axis, W, Xs[li], Es[li], y_l, dx_l, dw_l)
+        check["device_error"] = _lib.device_error()
 
+    # ---- per-kernel timing (each kernel alone) for the roofline object: cold (rotating inputs > L2) and warm L2
     pk = peaks()
-    per_op = {}
-    per_op["fprop"] = time_op(lambda i: bsmm.fprop(Xs[i % NSETS], W))
-    per_op["bprop"] = time_op(lambda i: bsmm.bprop(Es[i % NSETS], W))
-    per_op["updat"] = time_op(lambda i: bsmm.updat([Xs[i % NSETS]], [Es[i % NSETS]]))
+    cold = time_three_ops(torch, _lib, bsmm, W, Xs, Es, pk, reps=50)
+    warm = time_three_ops(torch, _lib, bsmm, W, Xs, Es, pk, reps=50, warm_l2=True)
+    per_op = {k: v["ms"] for k, v in cold.items()}
     clocks = None
     if sampler:                      # sampled from the start of the timed region to the end of the per-kernel loops
         clocks = sampler.stop()
@@ -335,14 +429,19 @@ def main():
         roof = {"bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"]}
     else:
         roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and abs(args.density - 0.25) < 1e-9:
-        traffic = json.load(open(tpath)).get(kernels[dom])
-    roof.update({"kernel": "%s (%s)" % (dom, kernels[dom]), "traffic": traffic, "peak_source": pk["source"],
-                 "per_op_ms": per_op,
-                 "per_op_tflops": {k: flops_op / (v * 1e-3) / 1e12 for k, v in per_op.items()},
-                 "per_op_frac_tensor_peak": {k: flops_op / (v * 1e-3) / 1e12 / pk["tf_burst"] for k, v in per_op.items()},
+    traffic, traffic_src = None, None
+    for tname in ("r2_traffic.json", "r1_traffic.json"):       # dram bytes per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and abs(args.density - 0.25) < 1e-9:
+            traffic = json.load(open(tpath)).get(kernels[dom])
+            if traffic is not None:
+                traffic_src = "profiles/" + tname
+                break
+    roof.update({"kernel": "%s (%s)" % (dom, kernels[dom]), "traffic": traffic, "traffic_source": traffic_src,
+                 "peak_source": pk["source"], "per_op_ms": per_op, "per_op_ms_warm_l2": {k: v["ms"] for k, v in warm.items()},
+                 "per_op_tflops": {k: v["tflops"] for k, v in cold.items()},
+                 "per_op_frac_tensor_peak": {k: v["frac_tensor_peak"] for k, v in cold.items()},
+                 "per_op_frac_hbm_peak": {k: v["frac_hbm_peak"] for k, v in cold.items()},
                  "algorithmic_flops_per_launch": flops_op, "algorithmic_bytes_per_launch": bytes_op})
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -390,8 +489,6 @@ def main():
         yd, dxd, dwd = y.detach(), x.grad, w_param.grad
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(done)
-            if d2h_done[j] is not None:
-                pass                                    # host buffers are reused in order on this one stream
             hy.copy_(yd, non_blocking=True)
             hdx.copy_(dxd, non_blocking=True)
             hdw.copy_(dwd, non_blocking=True)
@@ -422,28 +519,73 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    h2d_b = int(hx[0].numel() * 2 + he[0].numel() * 2)
+    d2h_b = int(hy.numel() * 2 + hdx.numel() * 2 + hdw.numel() * 2)
     e2e = {"value": flops_step_gpu * world / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-           "h2d_bytes_per_step": int(hx[0].numel() * 2 + he[0].numel() * 2),
-           "d2h_bytes_per_step": int(hy.numel() * 2 + hdx.numel() * 2 + hdw.numel() * 2),
+           "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
            "ms_per_step": e2e_ms, "host_buffers_numa_local": old_affinity is not None,
+           "pcie_gbs": {"h2d_plus_d2h_per_step_over_time": (h2d_b + d2h_b) / (e2e_ms * 1e-3) / 1e9},
            "api": "BlocksparseMatMul.__call__ + autograd backward; pinned host buffers; H2D / kernels / D2H on three streams, double-buffered"}
+    del hx, he, hy, hdx, hdw, dev_x, dev_e
 
-    sweep = None
-    if args.sweep and rank == 0:
+    # ---- BASELINE configs[4]: strong scaling, global N = 32768 split over the ranks (all ranks take part)
+    extras = {}
+    if not args.no_extras:
+        Ng = 32768
+        n_loc = Ng // world
+        reps = 1 if n_loc <= N else n_loc // N
+        # the shard is `reps` concatenated copies of the 4096-row synthetic sets (fresh rows would only change the data)
+        xs5 = [torch.cat([Xs[(j + r) % NSETS] for r in range(reps)], 0 if args.axis else 1) for j in range(2 if reps > 2 else NSETS)]
+        es5 = [torch.cat([Es[(j + r) % NSETS] for r in range(reps)], 0 if args.axis else 1) for j in range(2 if reps > 2 else NSETS)]
+        step5 = make_step(bsmm, W, xs5, es5)
+        for i in range(3):
+            step5(i)
+        ms5, _ = timed(step5, 20)
+        extras["cfg5_strong"] = {"global_N": Ng, "N_per_gpu": n_loc, "ms_per_step": ms5,
+                                 "value": 3 * 2.0 * bsmm.blocks * BS * BS * Ng / (ms5 * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                 "note": "BASELINE configs[4] as written: fixed global minibatch; compare across --gpus runs"}
+        del xs5, es5
+
+    if rank == 0 and not args.no_extras:
+        from blocksparse_b200.layouts import barabasi_albert_layout
         sweep = {}
         for d in (0.05, 0.10, 0.25, 0.50, 1.00):
             b2 = BlocksparseMatMul(make_layout(d), block_size=BS, feature_axis=args.axis)
             W2 = (torch.randn(b2.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
-            fl = 2.0 * b2.blocks * BS * BS * N
-            by = 2.0 * (C * N + K * N) + 2.0 * b2.blocks * BS * BS
-            r = {}
-            for name, fn in [("fprop", lambda i: b2.fprop(Xs[i % NSETS], W2)), ("bprop", lambda i: b2.bprop(Es[i % NSETS], W2)),
-                             ("updat", lambda i: b2.updat([Xs[i % NSETS]], [Es[i % NSETS]]))]:
-                m = time_op(fn, reps=10)
-                r[name] = {"ms": m, "tflops": fl / (m * 1e-3) / 1e12, "frac_tensor_peak": fl / (m * 1e-3) / 1e12 / pk["tf_burst"],
-                           "hbm_gbs": by / (m * 1e-3) / 1e9, "frac_hbm_peak": by / (m * 1e-3) / 1e9 / pk["hbm"]}
+            r = time_three_ops(torch, _lib, b2, W2, Xs, Es, pk, reps=20)
+            rw = time_three_ops(torch, _lib, b2, W2, Xs, Es, pk, reps=20, warm_l2=True)
+            for k in r:
+                r[k]["ms_warm_l2"] = rw[k]["ms"]
             r["nnz_blocks"] = b2.blocks
             sweep["%d%%" % round(d * 100)] = r
+        extras["density_sweep"] = sweep
+        var = {}
+        b2 = BlocksparseMatMul(barabasi_albert_layout(C // BS, args.density, np.random.default_rng(SEED + 1)), block_size=BS, feature_axis=args.axis)
+        W2 = (torch.randn(b2.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
+        var["barabasi_albert_skewed"] = dict(time_three_ops(torch, _lib, b2, W2, Xs, Es, pk), nnz_blocks=b2.blocks,
+                                             max_col_blocks=int(b2.layout.sum(0).max()), mean_col_blocks=float(b2.layout.sum(0).mean()))
+        b2 = BlocksparseMatMul(lay, block_size=BS, feature_axis=1 - args.axis)
+        xt = [x.t().contiguous() for x in Xs]
+        et = [e.t().contiguous() for e in Es]
+        var["feature_axis_%d" % (1 - args.axis)] = dict(time_three_ops(torch, _lib, b2, W, xt, et, pk), nnz_blocks=b2.blocks)
+        del xt, et
+        b2 = BlocksparseMatMul(make_layout(args.density, C // 64, K // 64), block_size=64, feature_axis=args.axis)
+        W2 = (torch.randn(b2.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
+        var["block_size_64"] = dict(time_three_ops(torch, _lib, b2, W2, Xs, Es, pk), nnz_blocks=b2.blocks)
+        var["fp16"] = dict(time_three_ops(torch, _lib, bsmm, W.half(), [x.half() for x in Xs], [e.half() for e in Es], pk), nnz_blocks=bsmm.blocks)
+        extras["variants"] = var
+        # BASELINE configs[3]: block-size sweep at 20 % density, N = 2048
+        cfg4 = {}
+        x4 = [x[:2048].contiguous() if args.axis else x[:, :2048].contiguous() for x in Xs]
+        e4 = [e[:2048].contiguous() if args.axis else e[:, :2048].contiguous() for e in Es]
+        for bs4 in (8, 16, 32, 64):
+            b2 = BlocksparseMatMul(make_layout(0.20, C // bs4, K // bs4, seed=1238), block_size=bs4, feature_axis=args.axis)
+            W2 = (torch.randn(b2.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
+            cfg4["bs%d" % bs4] = dict(time_three_ops(torch, _lib, b2, W2, x4, e4, pk, reps=10), nnz_blocks=b2.blocks)
+        extras["cfg4_block_size_sweep"] = {"config": "4096x4096 density 20% N=2048 bf16 axis %d" % args.axis, "results": cfg4}
+        del x4, e4
+        extras["cfg3_attention"] = bench_attention(torch, _lib, dev, pk)
+        extras["device_error_after_extras"] = _lib.device_error()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -454,13 +596,49 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": launches[0], "kernels": kernels, "nnz_blocks": bsmm.blocks,
-                "frac_density_scaled_tensor_peak": value / world / pk["tf_sust"]}
-        if sweep:
-            line["density_sweep"] = sweep
+                "gpu_launches": n_launches, "kernels": kernels, "nnz_blocks": bsmm.blocks,
+                "frac_density_scaled_tensor_peak": value / world / pk["tf_sust"], "check": check}
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_attention(torch, _lib, dev, pk):
+    """BASELINE configs[2]: heads 16, ctx 4096, bs 64, local+strided causal layout, batch 4, head_state 64, fp16."""
+    from blocksparse_b200 import BlocksparseTransformer
+    from blocksparse_b200.layouts import local_strided_layout
+    batch, heads, hs, bs, nb = 4, 16, 64, 64, 64
+    lay = local_strided_layout(nb)
+
+    def causal(blk_shape, head_idx, qry_idx, key_idx, blk_idx):
+        m = np.ones(blk_shape, dtype=bool)
+        return np.tril(m) if qry_idx == key_idx else m
+
+    bst = BlocksparseTransformer(lay, bs, heads=heads, mask_callback=causal)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    Q, Kt, V, DY = ((torch.rand((batch, nb * bs, heads * hs), generator=gen, device=dev) * 2 - 1).half() for _ in range(4))
+    scale = 1.0 / np.sqrt(hs)
+    S = bst._nt(Q, Kt, torch.bfloat16)
+    P = bst._softmax(S, scale, True, None, torch.float16)
+    DP = bst._nt(DY, V, torch.float16)
+    bh = batch * heads
+    gemm_flops = 2.0 * bst.blocks * bs * bs * hs * bh
+    sparse_bytes = bst.blocks * bs * bs * 2.0 * bh
+    dense_bytes = nb * bs * hs * 2.0 * bh
+    ops = [("nt", lambda i: bst._nt(Q, Kt, torch.bfloat16), gemm_flops, 2 * dense_bytes + sparse_bytes),
+           ("masked_softmax", lambda i: bst._softmax(S, scale, True, None, torch.float16), 0.0, 2 * sparse_bytes),
+           ("nn", lambda i: bst._xn(P, V, False), gemm_flops, sparse_bytes + 2 * dense_bytes),
+           ("tn", lambda i: bst._xn(P, DY, True), gemm_flops, sparse_bytes + 2 * dense_bytes),
+           ("softmax_grad", lambda i: bst._softmax_grad(DP, P, scale), 0.0, 3 * sparse_bytes)]
+    if hasattr(bst, "attention"):
+        ops.append(("fused_attention", lambda i: bst.attention(Q, Kt, V, scale=scale), 2 * gemm_flops, 4 * dense_bytes))
+    out = {"config": "batch 4 heads 16 head_state 64 ctx 4096 bs 64, %d blocks, fp16 in / bf16 scores" % bst.blocks}
+    for name, fn, fl, by in ops:
+        ms = time_loop(torch, fn, 10)
+        out[name] = op_record(ms, fl, by, pk, _lib.last_kernel())
+    out["forward_chain_ms"] = out["nt"]["ms"] + out["masked_softmax"]["ms"] + out["nn"]["ms"]
+    return out
 
 
 if __name__ == "__main__":

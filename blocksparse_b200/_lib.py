@@ -24,7 +24,8 @@ SIGNATURES = {
     "bsmm_device_info": (_i, [_c.POINTER(_i)] * 3),
     "bsmm_device_error": (_i, []),
     "bsmm_set_wait_timeout_ms": (_i, [_i, _i]),
-    "bsmm_xprop": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "bsmm_debug_trace": (_i, [_vp, _i]),
+    "bsmm_xprop": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "bsmm_updat": (_i, [_i, _i, _i, _i, _vp, _i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i,
                         _vp, _i, _f, _f, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "bsmm_gate_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),

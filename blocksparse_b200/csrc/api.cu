@@ -34,6 +34,13 @@ int bsmm_device_error(void) {
   return v ? v : wv;
 }
 
+int bsmm_debug_trace(unsigned long long* out, int n) {
+  unsigned long long* b = xprop2_trace_buffer();
+  if (!b || !out || n <= 0 || n > 256 * 8) return fail(BSMM_E_ARG, "bsmm_debug_trace: tracing is off (BSMM_TRACE) or bad arguments");
+  cudaError_t e = cudaMemcpy(out, b, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? 0 : fail((int)e, "bsmm_debug_trace: %s", cudaGetErrorString(e));
+}
+
 int bsmm_set_wait_timeout_ms(int ms, int trap) {
   if (ms <= 0) return fail(BSMM_E_ARG, "bsmm_set_wait_timeout_ms: ms must be positive");
   const unsigned long long ns = (unsigned long long)ms * 1000000ull;
@@ -57,6 +64,7 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
                const void* x, const void* w, void* y, int N,
                const float* gate,
                const int32_t* sched, int sched_tiles, int sched_tile_blocks, int sched_groups_off,
+               int sched_list_off, int sched_ctas, int sched_ntiles,
                int flags, void* stream) {
   if (int e = check_bsize_axis(bsize, axis)) return e;
   if (!lut || !x || !w || !y) return fail(BSMM_E_ARG, "bsmm_xprop: null pointer");
@@ -67,7 +75,12 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
   cudaStream_t s = (cudaStream_t)stream;
 
   if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
-    int rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_tiles, sched_tile_blocks, sched_groups_off, s);
+    int rc;
+    if (sched_list_off > 0 && bsize == 32 && gate == nullptr)     // pair schedule (lut.py:build_pair_schedule) -> csrc/tc_xprop2.cuh
+      rc = tc_xprop2(dtype, axis, bprop, n_out, n_in, blocks, x, w, y, N, sched, sched_tiles, sched_tile_blocks >> 8,
+                     sched_groups_off, sched_list_off, sched_ctas, sched_ntiles, s);
+    else
+      rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_tiles, sched_tile_blocks, sched_groups_off, s);
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC)
       return fail(BSMM_E_ARG, "bsmm_xprop: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());

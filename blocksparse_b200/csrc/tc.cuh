@@ -53,6 +53,34 @@ inline int make_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t in
   return 0;
 }
 
+// Encoding a CUtensorMap costs a few microseconds of host time and the same (pointer, shape) tuples come back every
+// training step, so the encoded descriptors are kept in a small thread-local cache (round-robin replacement).  The
+// descriptors are still passed to the kernels by value (__grid_constant__), so launches stay CUDA-graph capturable.
+struct TmapKey {
+  const void* base; uint64_t inner, outer, pitch; uint32_t box_inner, box_outer; int dtype, swz, dev;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && pitch == o.pitch && box_inner == o.box_inner &&
+           box_outer == o.box_outer && dtype == o.dtype && swz == o.swz && dev == o.dev;
+  }
+};
+constexpr int TMAP_CACHE_SLOTS = 32;
+struct TmapCache { TmapKey key[TMAP_CACHE_SLOTS]; CUtensorMap map[TMAP_CACHE_SLOTS]; int used = 0, next = 0; };
+inline int cached_tmap_2d(CUtensorMap* m, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_elems,
+                          uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
+  static thread_local TmapCache cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const TmapKey k = {base, inner, outer, row_pitch_elems, box_inner, box_outer, dtype, (int)swz, dev};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == k) { *m = cache.map[i]; return 0; }
+  if (int e = make_tmap_2d(m, dtype, base, inner, outer, row_pitch_elems, box_inner, box_outer, swz)) return e;
+  const int slot = cache.next;
+  cache.key[slot] = k; cache.map[slot] = *m;
+  cache.next = (slot + 1) % TMAP_CACHE_SLOTS;
+  if (cache.used < TMAP_CACHE_SLOTS) ++cache.used;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pipeline protocol.  One pipeline stage == one schedule GROUP (lut.py:build_tile_schedule): the
 // activation tile of one input block plus the <= WPS W blocks of the output tile that consume it, all
@@ -481,12 +509,12 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   XpropTmaps maps;
   const CUtensorMapSwizzle swz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   if (axis == 1) {
-    if (int e = make_tmap_2d(&maps.x, dtype, x, Cin, (uint64_t)N, Cin, bsize, 128, swz)) return e;
+    if (int e = cached_tmap_2d(&maps.x, dtype, x, Cin, (uint64_t)N, Cin, bsize, 128, swz)) return e;
   } else {       // (C, N): inner dim = minibatch; box = 64 columns x bs feature rows, 128-byte rows
-    if (int e = make_tmap_2d(&maps.x, dtype, x, (uint64_t)N, Cin, (uint64_t)N, 64, bsize, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    if (int e = cached_tmap_2d(&maps.x, dtype, x, (uint64_t)N, Cin, (uint64_t)N, 64, bsize, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
-  if (int e = make_tmap_2d(&maps.w, dtype, w, (uint64_t)bsize, (uint64_t)blocks * bsize, (uint64_t)bsize, bsize, bsize, swz)) return e;
-  if (int e = make_tmap_2d(&maps.y, dtype, y, Cout, (uint64_t)N, Cout, bsize, 128, swz)) return e;
+  if (int e = cached_tmap_2d(&maps.w, dtype, w, (uint64_t)bsize, (uint64_t)blocks * bsize, (uint64_t)bsize, bsize, bsize, swz)) return e;
+  if (int e = cached_tmap_2d(&maps.y, dtype, y, Cout, (uint64_t)N, Cout, bsize, 128, swz)) return e;
 
   XpropTcParams p;
   p.sched = sched;
@@ -528,6 +556,7 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
 
 }  // namespace bsmm
 
+#include "tc_xprop2.cuh"
 #include "tc_updat.cuh"
 #include "softmax.cuh"
 #include "tc_bst.cuh"

@@ -400,14 +400,14 @@ inline int tc_bst_nt(int dtype, int c_dtype, int bsize, const int32_t* items, in
   if (!bst_tc_applicable(dtype, bsize, head_state, a, b, c)) return TC_NOT_APPLICABLE;
   const uint64_t S = (uint64_t)heads * head_state;
   BstNtTmaps maps;
-  if (int e = make_tmap_2d(&maps.a, dtype, a, S, (uint64_t)batch * ctx_blks_a * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (int e = make_tmap_2d(&maps.b, dtype, b, S, (uint64_t)batch * ctx_blks_b * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = cached_tmap_2d(&maps.a, dtype, a, S, (uint64_t)batch * ctx_blks_a * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = cached_tmap_2d(&maps.b, dtype, b, S, (uint64_t)batch * ctx_blks_b * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   BstNtParams p;
   p.items = items; p.n_items = n_items; p.lut_heads = lut_heads; p.batch = batch; p.heads = heads; p.blocks = blocks;
   p.head_state = head_state; p.ctx_rows_a = ctx_blks_a * 64; p.ctx_rows_b = ctx_blks_b * 64; p.c = c;
   const unsigned long long c_rows = (unsigned long long)batch * heads * blocks * 64;
   p.tma_store = (c_dtype != BSMM_F32 && c_rows < (1ull << 31)) ? 1 : 0;
-  if (p.tma_store) { if (int e = make_tmap_2d(&maps.c, c_dtype, c, 64, c_rows, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e; }
+  if (p.tma_store) { if (int e = cached_tmap_2d(&maps.c, c_dtype, c, 64, c_rows, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e; }
   else maps.c = maps.a;
   const size_t smem = (size_t)BST_NT_STAGES * 3 * BST_TILE + 4 * BST_TILE;
   const long long total = (long long)batch * heads * n_items;
@@ -435,8 +435,8 @@ inline int tc_bst_xn(int a_dtype, int dtype, int bsize, int transpose_a, const i
   if ((unsigned long long)batch * heads * blocks * 64 >= (1ull << 31)) { fail(0, "sparse tensor too large for one tensor map"); return TC_NOT_APPLICABLE; }
   const uint64_t S = (uint64_t)heads * head_state;
   BstXnTmaps maps;
-  if (int e = make_tmap_2d(&maps.a, dtype, a, 64, (uint64_t)batch * heads * blocks * 64, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (int e = make_tmap_2d(&maps.b, dtype, b, S, (uint64_t)batch * ctx_blks_b * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = cached_tmap_2d(&maps.a, dtype, a, 64, (uint64_t)batch * heads * blocks * 64, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (int e = cached_tmap_2d(&maps.b, dtype, b, S, (uint64_t)batch * ctx_blks_b * 64, S, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   BstXnParams p;
   p.lut = lut; p.order = order; p.lut_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_c + blocks) : 0; p.n_out = ctx_blks_c; p.lut_heads = lut_heads;
   p.batch = batch; p.heads = heads; p.blocks = blocks; p.head_state = head_state;

@@ -265,11 +265,11 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   const CUtensorMapSwizzle bswz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int i = 0; i < pcount; ++i) {
     if (axis == 1) {
-      if (int e = make_tmap_2d(&maps.x[i], dtype, xs[i], C, (uint64_t)N, C, 64, UPDAT_KCHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-      if (int e = make_tmap_2d(&maps.dy[i], dtype, dys[i], K, (uint64_t)N, K, bsize, UPDAT_KCHUNK, bswz)) return e;
+      if (int e = cached_tmap_2d(&maps.x[i], dtype, xs[i], C, (uint64_t)N, C, 64, UPDAT_KCHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+      if (int e = cached_tmap_2d(&maps.dy[i], dtype, dys[i], K, (uint64_t)N, K, bsize, UPDAT_KCHUNK, bswz)) return e;
     } else {       // (features, N): inner dim = minibatch, 64 columns = 128-byte rows
-      if (int e = make_tmap_2d(&maps.x[i], dtype, xs[i], (uint64_t)N, C, (uint64_t)N, UPDAT_KCHUNK, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-      if (int e = make_tmap_2d(&maps.dy[i], dtype, dys[i], (uint64_t)N, K, (uint64_t)N, UPDAT_KCHUNK, bsize, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+      if (int e = cached_tmap_2d(&maps.x[i], dtype, xs[i], (uint64_t)N, C, (uint64_t)N, UPDAT_KCHUNK, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+      if (int e = cached_tmap_2d(&maps.dy[i], dtype, dys[i], (uint64_t)N, K, (uint64_t)N, UPDAT_KCHUNK, bsize, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
     }
   }
   UpdatTcParams p;

@@ -52,6 +52,8 @@ struct Xprop2Params {
   void* y;
   long long y_pitch;         // elements
   int N;
+  unsigned long long* trace; // tuning aid (BSMM_TRACE): CTA 0 records clock64 at 5 pipeline events of its first 256 groups
+  int ablate;                // tuning aid (BSMM_ABLATE): 1 no MMAs, 2 no TMA loads, 4 no epilogue work, 8 no W loads, 16 no X loads
 };
 
 template <class Cfg, bool BF16>
@@ -66,7 +68,7 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
   uint8_t* sStage = smem;                          // XS x (activation tile | WPS W blocks)
   uint8_t* sO = smem + XS * STAGE_BYTES;           // STG x output-block staging
   __shared__ uint64_t full[XS], empty[XS], acc_full, acc_empty, turn[NP];
-  __shared__ __align__(16) int4 cmd[XS][16];       // per run: (B descriptor low word, D tmem address, idesc, run count)
+  __shared__ __align__(16) int2 cmd[XS][16];       // per run: (B descriptor low word, accumulator column | N/8 << 12 | run count << 20)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   volatile int* abort_flag = &abort_s;
@@ -96,7 +98,6 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
     // ================================ TMA producers ================================
     uint32_t gbase = 0;                   // groups of earlier tiles
     bool alive = true;
-    const uint32_t p_idesc0 = ptx::make_idesc_f16(BF16, p.axis0 != 0, !p.bprop, 128, 0);
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
                    cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0])), stage0 = ptx::opaque(ptx::smem_u32(sStage));
     // fprop: B = W[c][k] read as K x N, N contiguous (MN-major), next 32-column block = next slot (LBO = WBYTES)
@@ -121,20 +122,31 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
         const int counts = __shfl_sync(0xffffffffu, cur, 1);
         const int n_w = counts & 0xff, nr0 = (counts >> 8) & 0xff, nr1 = (counts >> 16) & 0xff;
         if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(empty0 + st * 8, ((pj / HS) & 1) ^ 1, abort_flag))) { g_tc_error = 1; alive = false; break; }
+        if (p.trace && blockIdx.x == 0 && lane == 0 && gc < 256) p.trace[gc * 8 + 0] = clock64();
         if (lane >= 16) {
           const int r = lane - 16;                           // 0..7 half 0, 8..15 half 1
           const int nr = r < 8 ? nr0 : nr1;
           if ((r & 7) < nr || (r & 7) == 0) {
             const uint32_t pk = (uint32_t)cur;
-            ptx::st_shared_v4(cmd0 + st * (16 * 16) + r * 16,
-                              (int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (pk & 0xfffu)),
-                              (int)(tmem + ((pk >> 12) & 0x1ffu)),
-                              (int)(p_idesc0 | (((pk >> 21) & 0x3fu) << 17)),
-                              nr);
+            asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(cmd0 + st * (16 * 8) + r * 8),
+                         "r"((int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (pk & 0xfffu))),
+                         "r"((int)(((pk >> 12) & 0x1ffu) | (((pk >> 21) & 0x3fu) << 12) | ((uint32_t)nr << 20))) : "memory");
           }
         }
         __syncwarp();
         const uint32_t stage = stage0 + st * STAGE_BYTES, fbar = full0 + st * 8;
+        if (p.ablate & 26) {                       // timing ablations: drop some or all loads (results are garbage)
+          const bool no_x = p.ablate & (2 | 16), no_w = p.ablate & (2 | 8);
+          if (lane == 0) {
+            ptx::mbar_expect_tx_a(fbar, (no_x ? 0u : XBYTES) + (no_w ? 0u : (uint32_t)n_w * WBYTES));
+            if (!no_x) ptx::tma_load_2d_a(stage, &maps.x, fbar, in_pair * 64, nt * 128);
+          }
+          if (!no_w && lane >= 2 && lane < 2 + n_w)
+            ptx::tma_load_2d_a(stage + XBYTES + (lane - 2) * WBYTES, &maps.w, fbar, 0, cur * BS);
+          __syncwarp();
+          if (p.trace && blockIdx.x == 0 && lane == 0 && gc < 256) p.trace[gc * 8 + 1] = clock64();
+          continue;
+        }
         if (lane == 0) {
           ptx::mbar_expect_tx_a(fbar, XBYTES + (uint32_t)n_w * WBYTES);
           if (!p.axis0) {
@@ -147,6 +159,7 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
         if (lane >= 2 && lane < 2 + n_w)
           ptx::tma_load_2d_a(stage + XBYTES + (lane - 2) * WBYTES, &maps.w, fbar, 0, cur * BS);
         __syncwarp();
+        if (p.trace && blockIdx.x == 0 && lane == 0 && gc < 256) p.trace[gc * 8 + 1] = clock64();
       }
       gbase += n_groups;
     }
@@ -160,6 +173,7 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
                                      : ptx::make_smem_desc(ptx::smem_u32(sStage), 16, 1024, ptx::SWZ_128B);
     const uint32_t a_kstep16 = p.axis0 ? (16u * 128u) >> 4 : 2u;
     const uint32_t b_desc_hi = (uint32_t)(ptx::make_smem_desc(0, 16, 512, ptx::SWZ_64B) >> 32);
+    const uint32_t idesc0 = ptx::make_idesc_f16(BF16, p.axis0 != 0, !p.bprop, 128, 0);
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
                    cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0]));
     uint32_t tile_it = 0, gbase = 0;
@@ -177,45 +191,51 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
       for (; g < n_groups; g += NP) {
         const uint32_t st = iw + NP * js;
         if (!__all_sync(0xffffffffu, ptx::mbar_wait_a(full0 + st * 8, ph, abort_flag))) { g_tc_error = 4; alive = false; break; }
+        const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (gbase + g) < 256;
+        if (tr) p.trace[(gbase + g) * 8 + 2] = clock64();
         bool my_turn = true;
         if (NP > 1)
           my_turn = (iw == 0) ? (pj == 0 || ptx::mbar_wait(&turn[0], (pj - 1) & 1, abort_flag))
                               : ptx::mbar_wait(&turn[iw], pj & 1, abort_flag);
         if (!__all_sync(0xffffffffu, my_turn)) { g_tc_error = 5; alive = false; break; }
+        if (tr) p.trace[(gbase + g) * 8 + 3] = clock64();
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t a_lo = a_lo0 + st * (STAGE_BYTES >> 4);
-          const uint32_t cq = cmd0 + st * (16 * 16);
-          int4 c[16];
+          const uint32_t cq = cmd0 + st * (16 * 8);
+          int2 c[16];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; r += 2)
               asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(c[h * 8 + r].x), "=r"(c[h * 8 + r].y), "=r"(c[h * 8 + r].z), "=r"(c[h * 8 + r].w) : "r"(cq + (h * 8 + r) * 16));
-          const int n0 = c[0].w, n1 = c[8].w;
+                           : "=r"(c[h * 8 + r].x), "=r"(c[h * 8 + r].y), "=r"(c[h * 8 + r + 1].x), "=r"(c[h * 8 + r + 1].y) : "r"(cq + (h * 8 + r) * 8));
+          const int n0 = (int)((uint32_t)c[0].y >> 20), n1 = (int)((uint32_t)c[8].y >> 20);
           if (n0 > 4) {
 #pragma unroll
-            for (int r = 4; r < 8; ++r)
-              asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r].z), "=r"(c[r].w) : "r"(cq + r * 16));
+            for (int r = 4; r < 8; r += 2)
+              asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r + 1].x), "=r"(c[r + 1].y) : "r"(cq + r * 8));
           }
           if (n1 > 4) {
 #pragma unroll
-            for (int r = 12; r < 16; ++r)
-              asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r].z), "=r"(c[r].w) : "r"(cq + r * 16));
+            for (int r = 12; r < 16; r += 2)
+              asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(c[r].x), "=r"(c[r].y), "=r"(c[r + 1].x), "=r"(c[r + 1].y) : "r"(cq + r * 8));
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            if (p.ablate & 1) break;
             const int h = ks >> 1;
             const int nr = h ? n1 : n0;
             const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint32_t)(a_lo + ks * a_kstep16);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
               if (r >= nr) break;              // uniform branch: skipped runs cost nothing
-              const int4 cc = c[h * 8 + r];
+              const int2 cc = c[h * 8 + r];
               const uint64_t bdesc = ((uint64_t)b_desc_hi << 32) | (uint32_t)((uint32_t)cc.x + (ks & 1) * b_kstep16);
-              if (r == 0) ptx::mma_ss_a_fill((uint32_t)cc.y, adesc, bdesc, (uint32_t)cc.z, 1u);
-              else        ptx::mma_ss_a_use((uint32_t)cc.y, adesc, bdesc, (uint32_t)cc.z, 1u);
+              const uint32_t d_addr = tmem + ((uint32_t)cc.y & 0xfffu);
+              const uint32_t idesc = idesc0 | ((((uint32_t)cc.y >> 12) & 0x3fu) << 17);
+              if (r == 0) ptx::mma_ss_a_fill(d_addr, adesc, bdesc, idesc, 1u);
+              else        ptx::mma_ss_a_use(d_addr, adesc, bdesc, idesc, 1u);
             }
           }
           ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
@@ -225,6 +245,7 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
           }
         }
         __syncwarp();
+        if (tr) p.trace[(gbase + g) * 8 + 4] = clock64();
         ++pj;
         if (++js == HS) { js = 0; ph ^= 1; }
       }
@@ -259,6 +280,11 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
       asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
       if (*abort_flag) { g_tc_error = 6; break; }       // uniform across the epilogue threads
       ptx::tc_fence_after();
+      if (p.ablate & 4) {
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+        if (etid == 0) ptx::mbar_arrive(&acc_empty);
+        continue;
+      }
       if (p.axis0) {
         // Y is (K, N): lane = minibatch column, register j = output feature -> for every j a warp writes 32
         // consecutive 16-bit values (one 64-byte segment); no staging needed.
@@ -338,6 +364,15 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
   if (warp == NP) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
+inline unsigned long long* xprop2_trace_buffer() {
+  static unsigned long long* buf = [] {
+    unsigned long long* b = nullptr;
+    if (getenv("BSMM_TRACE") && cudaMalloc(&b, 256 * 8 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(b, 0, 256 * 8 * 8);
+    return b;
+  }();
+  return buf;
+}
+
 template <class Cfg, bool BF16>
 int launch_tc_xprop2(const Xprop2Params& p, const XpropTmaps& maps, int n_ctas, cudaStream_t s) {
   auto kern = tc_xprop2_kernel<Cfg, BF16>;
@@ -391,6 +426,9 @@ inline int tc_xprop2(int dtype, int axis, int bprop, int n_out, int n_in, int bl
   p.sched = sched; p.groups_off = groups_off; p.list_off = list_off; p.n_ktiles = sched_tiles;
   p.bprop = bprop; p.axis0 = axis == 0;
   p.y = y; p.y_pitch = axis == 0 ? (long long)N : (long long)Cout; p.N = N;
+  static const int ablate = [] { const char* e = getenv("BSMM_ABLATE"); return e ? atoi(e) : 0; }();
+  p.ablate = ablate;
+  p.trace = xprop2_trace_buffer();
   const bool bf = dtype == BSMM_BF16;
   switch (variant) {
     case 1: return bf ? launch_tc_xprop2<Xp2Sparse, true>(p, maps, n_ctas, s) : launch_tc_xprop2<Xp2Sparse, false>(p, maps, n_ctas, s);

@@ -38,6 +38,25 @@ def allreduce_dw(dw, group=None, average=False, async_op=False):
     return work if async_op else None
 
 
+def reserve_sms_for_nccl(n_sms=8, nccl_ctas=None):
+    """Leave `n_sms` SMs free of persistent tcgen05 CTAs so that a concurrent NCCL kernel has somewhere to run.
+
+    The block-sparse kernels are persistent grids sized to the whole GPU (one or two CTAs per SM, host-built tile lists).
+    An all-reduce issued on a side stream cannot start while such a grid owns every SM, and a compute kernel launched
+    while NCCL holds SMs runs its displaced CTAs as a second wave (profiles/r1_dist_diag.txt: zero overlap).  With a
+    margin, every persistent grid and its schedules are built for sm_count - n_sms SMs (csrc/common.cuh:sm_margin,
+    _lib.grid_sms) and NCCL is capped to as many CTAs (NCCL_MAX_CTAS), so both run side by side.
+    Must be called before the first block-sparse op and before the process group is created; explicit environment
+    settings win.  Returns the margin in effect.
+    """
+    import os
+    os.environ.setdefault("BSMM_SM_MARGIN", str(int(n_sms)))
+    margin = int(os.environ["BSMM_SM_MARGIN"])
+    if margin > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(int(nccl_ctas or margin)))
+    return margin
+
+
 class AllreduceStream(object):
     """Issue the dW all-reduce on a side stream ordered after the updat kernel by an event, so that the next layer's
     bprop overlaps it (the reference's AllreduceNccl pattern, src/nccl_op.cc:168,513)."""
@@ -57,6 +76,8 @@ class AllreduceStream(object):
         return dw
 
     def wait(self):
-        torch.cuda.current_stream().wait_stream(self.stream)
+        """Order the current stream after every reduction issued so far (device-side dependency, no host sync)."""
+        if self.pending:
+            torch.cuda.current_stream().wait_stream(self.stream)
         done, self.pending = self.pending, []
         return done

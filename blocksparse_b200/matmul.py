@@ -23,6 +23,12 @@ _WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))     # tuning aid: for
 _TILE_BLOCKS = {bs: (256 if occ == 2 else 512) // bs for bs, occ in _OCC.items()}
 # W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
 _SCHED_CACHE_MAX = 16
+# csrc/tc_xprop2.cuh variants: id -> (output blocks per tile, CTAs per SM, W slots per stage).  The family is OPT-IN
+# (BSMM_XPROP2=1..3 forces a variant, -1 picks by density): on B200 it measured 5-10 % slower than the single-block kernel
+# of csrc/tc.cuh at every density (profiles/r2_xprop2_study.txt has the timings, the ablations and the pipeline trace that
+# explain why), so 0 -- the default -- keeps csrc/tc.cuh.
+_X2_VARIANTS = {1: (8, 2, 4), 2: (8, 2, 8), 3: (16, 1, 12)}
+_X2_FORCE = int(os.environ.get("BSMM_XPROP2", "0"))
 _W_PER_GROUP = {32: 8, 64: 2 if _OCC[64] == 2 else 4}
 
 
@@ -135,6 +141,17 @@ class BlocksparseMatMul(object):
             self._dev[key] = d
         return d
 
+    def _xprop2_variant(self, dtype, gate):
+        """Which csrc/tc_xprop2.cuh variant serves this layout (0 = none: 64 x 64 blocks, fp32, dense layouts)."""
+        if self.bsize != 32 or dtype == torch.float32 or _X2_FORCE == 0:
+            return 0
+        if _X2_FORCE in _X2_VARIANTS:
+            return _X2_FORCE
+        density = self.blocks / float(self.CB * self.KB)
+        if density <= 0.12:
+            return 1
+        return 2 if density <= 0.45 else 0
+
     # ------------------------------------------------------------------ raw ops
     def fprop(self, x, w, gate=None, flags=0):
         return self._xprop(x, w, False, gate, flags)
@@ -159,7 +176,23 @@ class BlocksparseMatMul(object):
         d = self._device_luts(x.device)
         lut = d["bprop" if bprop else "fprop"]
         sched, sched_tiles, sched_off = None, 0, 0
-        if "xprop_sched" in d:
+        list_off = n_ctas = n_nt = 0
+        variant = self._xprop2_variant(x.dtype, gate) if "xprop_sched" in d else 0
+        if variant:
+            # pair schedule (csrc/tc_xprop2.cuh): wide activation tiles + host-built per-CTA tile lists
+            key = ("pair", bool(bprop), variant, N)
+            plan = d["xprop_sched"].get(key)
+            if plan is None:
+                tb, occ, wps = _X2_VARIANTS[variant]
+                n_nt = -(-N // 128)
+                n_ctas = _lib.grid_sms(x.device) * occ
+                n_kt = pick_tile_count(n_out, n_nt, n_ctas, tb)
+                arr, off, loff = self._luts.pair_schedule(bprop, tb, wps, n_kt, n_nt, n_ctas)
+                while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:
+                    d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
+                plan = d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), n_kt, off, loff, n_ctas, n_nt, tb | (variant << 8))
+            sched, sched_tiles, sched_off, list_off, n_ctas, n_nt, tile_arg = plan
+        elif "xprop_sched" in d:
             # tile count chosen so that (minibatch tiles) x (feature tiles) fills whole waves of the persistent grid
             tb = _TILE_BLOCKS[self.bsize]
             n_kt = pick_tile_count(n_out, -(-N // 128), d["cta_slots"], tb)
@@ -196,6 +229,7 @@ class BlocksparseMatMul(object):
                             x2.data_ptr(), w.data_ptr(), y2.data_ptr(), N,
                             _lib.ptr(gate),
                             _lib.ptr(sched), sched_tiles, tile_arg if sched is not None else 0, sched_off,
+                            list_off, n_ctas, n_nt,
                             flags, _lib.stream_ptr())
         _lib.check(rc, "bsmm_xprop")
         if self.axis == 0:

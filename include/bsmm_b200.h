@@ -82,6 +82,10 @@ int         bsmm_device_error(void);
  * the next CUDA call of the host reports the fault, so a starved or mis-sequenced kernel can never return partially
  * written outputs with rc 0.  trap = 0 keeps the context alive (the kernel exits early; poll bsmm_device_error()). */
 int         bsmm_set_wait_timeout_ms(int ms, int trap);
+/* Tuning aid: with BSMM_TRACE set in the environment, CTA 0 of the pair-schedule xprop kernel records clock64() at five
+ * pipeline events (producer: stage free, loads issued; issuer: stage full, turn taken, MMAs committed) of its first 256
+ * groups; this copies n <= 2048 words (8 per group) of the last launch to `out`. */
+int         bsmm_debug_trace(unsigned long long* out, int n);
 
 /* ---- block-sparse matmul -------------------------------------------------------- */
 
@@ -101,6 +105,9 @@ int         bsmm_set_wait_timeout_ms(int ms, int trap);
  *    per schedule group when it differs from the default: 2 or 4 select the deeper-pipeline variants used for
  *    layouts below ~12 % / ~37 % density), group records starting at int32 index sched_groups_off; NULL selects
  *    the CUDA-core kernels.
+ *    Pair schedule (32 x 32 blocks, lut.py:build_pair_schedule): sched_list_off > 0 gives the int32 index of the
+ *    per-CTA tile lists that follow the group records (built for sched_ctas CTAs and sched_ntiles = ceil(N/128)
+ *    minibatch tiles) and bits 8.. of sched_tile_blocks select the kernel variant (1 sparse, 2 mid, 3 wide tiles).
  * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).  With a gate the call runs on the
  *    CUDA-core kernels; for 16-bit weights call bsmm_gate_weights first and pass gate = NULL to stay on tcgen05.
  */
@@ -109,6 +116,7 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
                const void* x, const void* w, void* y, int N,
                const float* gate,
                const int32_t* sched, int sched_tiles, int sched_tile_blocks, int sched_groups_off,
+               int sched_list_off, int sched_ctas, int sched_ntiles,
                int flags, void* stream);
 
 /*

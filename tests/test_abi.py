@@ -41,9 +41,9 @@ def test_binding_covers_every_declared_symbol():
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.load()
     # block size 12 is rejected before anything touches the device
-    rc = lib.bsmm_xprop(_lib.F32, 0, 12, 0, None, 1, 1, 1, None, None, None, 4, None, None, 0, 0, 0, 0, None)
+    rc = lib.bsmm_xprop(_lib.F32, 0, 12, 0, None, 1, 1, 1, None, None, None, 4, None, None, 0, 0, 0, 0, 0, 0, 0, None)
     assert rc == -2 and b"block size" in lib.bsmm_last_error()
-    rc = lib.bsmm_xprop(_lib.F32, 0, 32, 0, None, 1, 1, 1, None, None, None, 4, None, None, 0, 0, 0, 0, None)
+    rc = lib.bsmm_xprop(_lib.F32, 0, 32, 0, None, 1, 1, 1, None, None, None, 4, None, None, 0, 0, 0, 0, 0, 0, 0, None)
     assert rc == -3
     with pytest.raises(ValueError):
         _lib.check(rc, "bsmm_xprop")
