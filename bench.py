@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="(kept for compatibility: the sweep is on by default)")
     ap.add_argument("--no-extras", action="store_true", help="headline only: no sweep / variants / cfg3 / cfg4 / cfg5 sub-records")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--sm-margin", type=int, default=None, help="SMs left free for NCCL when N>1 (default 8; BSMM_SM_MARGIN wins)")
+    ap.add_argument("--sm-margin", type=int, default=None, help="SMs left free for NCCL when N>1 (default 8 at 2 GPUs, 12 beyond; BSMM_SM_MARGIN wins)")
     ap.add_argument("--blocking-allreduce", action="store_true", help="round-1 behaviour: all-reduce on the compute stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -313,7 +313,8 @@ def main():
     from blocksparse_b200 import dist as bdist
     margin = 0
     if world > 1 and not args.blocking_allreduce:
-        margin = bdist.reserve_sms_for_nccl(8 if args.sm_margin is None else args.sm_margin)
+        # measured (profiles/r2_scaling.txt): 8 SMs hide the 17 MB fp32 all-reduce at 2 GPUs, 8 GPUs need 12
+        margin = bdist.reserve_sms_for_nccl((8 if world <= 2 else 12) if args.sm_margin is None else args.sm_margin)
     import torch
     import torch.distributed as dist
     from blocksparse_b200 import BlocksparseMatMul, _lib
@@ -339,7 +340,7 @@ def main():
     side = bdist.AllreduceStream(dev) if (world > 1 and not args.blocking_allreduce) else None
     config["dw_dtype"] = "fp32" if world > 1 else "bf16"
     config["allreduce"] = ("none (1 GPU)" if world == 1 else "blocking on the compute stream" if side is None else
-                           "side stream, overlaps the next step's fprop/bprop; %d SMs left to NCCL (NCCL_MAX_CTAS=%s)"
+                           "side stream, one reduction in flight, overlaps the next step's kernels; %d SMs left to NCCL (NCCL_MAX_CTAS=%s)"
                            % (margin, os.environ.get("NCCL_MAX_CTAS")))
 
     def make_step(op, w, xs, es):
@@ -347,11 +348,12 @@ def main():
             x, e = xs[i % len(xs)], es[i % len(es)]
             y = op.fprop(x, w)
             dx = op.bprop(e, w)
-            if side is not None:
-                side.wait()                       # the previous step's reduction is ordered before this updat
             dw = op.updat([x], [e], dw_dtype=dw_dtype)
             launches[0] += 3
             if side is not None:
+                # at most one reduction in flight: the previous one (whose consumer would be the optimizer) is ordered
+                # before this one is issued, so it overlaps a whole step of fprop / bprop / updat
+                side.wait()
                 side.reduce(dw)
             else:
                 bdist.allreduce_dw(dw)            # no-op at world size 1
@@ -546,7 +548,7 @@ def main():
                                  "note": "BASELINE configs[4] as written: fixed global minibatch; compare across --gpus runs"}
         del xs5, es5
 
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:       # single-GPU sub-records: part of the N=1 line only
         from blocksparse_b200.layouts import barabasi_albert_layout
         sweep = {}
         for d in (0.05, 0.10, 0.25, 0.50, 1.00):
@@ -582,7 +584,7 @@ def main():
             b2 = BlocksparseMatMul(make_layout(0.20, C // bs4, K // bs4, seed=1238), block_size=bs4, feature_axis=args.axis)
             W2 = (torch.randn(b2.w_shape, generator=gen, device=dev) * 0.01).to(dtype)
             cfg4["bs%d" % bs4] = dict(time_three_ops(torch, _lib, b2, W2, x4, e4, pk, reps=10), nnz_blocks=b2.blocks)
-        extras["cfg4_block_size_sweep"] = {"config": "4096x4096 density 20% N=2048 bf16 axis %d" % args.axis, "results": cfg4}
+        extras["cfg4_block_size_sweep"] = {"config": "4096x4096 density 20%% N=2048 bf16 axis %d" % args.axis, "results": cfg4}
         del x4, e4
         extras["cfg3_attention"] = bench_attention(torch, _lib, dev, pk)
         extras["device_error_after_extras"] = _lib.device_error()

@@ -76,11 +76,12 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
 
   if (!(flags & BSMM_FLAG_FORCE_GENERIC)) {
     int rc;
-    if (sched_list_off > 0 && bsize == 32 && gate == nullptr)     // pair schedule (lut.py:build_pair_schedule) -> csrc/tc_xprop2.cuh
-      rc = tc_xprop2(dtype, axis, bprop, n_out, n_in, blocks, x, w, y, N, sched, sched_tiles, sched_tile_blocks >> 8,
+    if ((sched_tile_blocks >> 16) & 1)       // pair schedule (lut.py:build_pair_schedule) -> csrc/tc_xprop2.cuh
+      rc = tc_xprop2(dtype, axis, bprop, n_out, n_in, blocks, x, w, y, N, sched, sched_tiles, (sched_tile_blocks >> 8) & 0xff,
                      sched_groups_off, sched_list_off, sched_ctas, sched_ntiles, s);
-    else
-      rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_tiles, sched_tile_blocks, sched_groups_off, s);
+    else                                      // sched_list_off = optional tile order table (heaviest first) for sched_ntiles minibatch tiles
+      rc = tc_xprop(dtype, axis, bsize, bprop, lut, n_out, n_in, blocks, x, w, y, N, gate, sched, sched_tiles, sched_tile_blocks & 0xffff,
+                    sched_groups_off, sched_list_off, sched_ntiles, s);
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC)
       return fail(BSMM_E_ARG, "bsmm_xprop: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());

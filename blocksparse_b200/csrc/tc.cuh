@@ -18,6 +18,7 @@
 //   last 4 warps      epilogue: tcgen05.ld -> 16-bit -> swizzled smem staging -> TMA store, then clear the lanes
 #pragma once
 #include <cuda.h>
+#include <atomic>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -134,6 +135,75 @@ template <class Cfg> constexpr int xprop_threads() { return (2 * Cfg::NP + 4) * 
 // sticky device-side error word: a kernel whose bounded wait timed out stores a non-zero code here
 __device__ int g_tc_error = 0;
 
+// ---- dynamic tile queue -------------------------------------------------------------------------
+// The persistent grids used to deal tile t to CTA t mod grid.  That is only optimal when every CTA of the grid is
+// resident from the first cycle: when a concurrent kernel (the NCCL all-reduce of the previous step's dW) holds a few
+// SMs, the displaced CTAs start after a first-wave CTA retires and the kernel takes twice as long.  Now CTAs pull tile
+// indices from a global counter (one atomicAdd per tile) in a host-chosen order (heaviest tiles first for skewed
+// layouts): late CTAs simply take fewer tiles.  Results do not depend on which CTA computes a tile, so they stay
+// bit-reproducible.  One counter pair per launch, taken round-robin from a pool; the last CTA to leave resets its slot.
+constexpr int TILE_RING = 4;
+constexpr int TILE_COUNTER_SLOTS = 64;
+__device__ int g_tile_counters[TILE_COUNTER_SLOTS][2];
+// BSMM_TILE_QUEUE=dynamic turns the global-counter queue on (blocksparse_b200.dist.reserve_sms_for_nccl does it for
+// multi-GPU runs); the default is the static deal tile k of a CTA = blockIdx.x + k * gridDim.x, which measured 4-8 % faster
+// when the grid has the GPU to itself (profiles/r2_tile_queue.txt).
+inline bool static_tiles() {
+  static const bool v = [] { const char* e = getenv("BSMM_TILE_QUEUE"); return !(e && (e[0] == 'd' || e[0] == 'D')); }();
+  return v;
+}
+inline bool static_order() { static const bool v = [] { const char* e = getenv("BSMM_NATURAL_ORDER"); return e && atoi(e) != 0; }(); return v || static_tiles(); }
+inline int* next_tile_counter() {
+  static thread_local int* base[64] = {};              // per device: the symbol lives in every device's module image
+  static std::atomic<unsigned> global_id{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int*& b = base[dev & 63];
+  if (!b) { void* ptr = nullptr; if (cudaGetSymbolAddress(&ptr, g_tile_counters) != cudaSuccess) return nullptr; b = (int*)ptr; }
+  const unsigned id = global_id.fetch_add(1, std::memory_order_relaxed);
+  return b + 2 * (id % TILE_COUNTER_SLOTS);
+}
+struct TileQueue {
+  int ring[TILE_RING];
+  uint64_t ready[TILE_RING], freed[TILE_RING];
+};
+__device__ __forceinline__ void tile_queue_init(TileQueue* q, int n_warps) {      // every warp of the CTA reads every slot
+  for (int i = 0; i < TILE_RING; ++i) { ptx::mbar_init(&q->ready[i], 1); ptx::mbar_init(&q->freed[i], n_warps); }
+}
+// Reader side, called by every warp of every role with the same running tile count k: the k-th tile of this CTA, or
+// -1 when the queue is drained (or a wait timed out).
+__device__ __forceinline__ int tile_queue_next(TileQueue* q, uint32_t k, int lane, volatile int* abort_flag) {
+  const uint32_t slot = k % TILE_RING;
+  if (!ptx::mbar_wait(&q->ready[slot], (k / TILE_RING) & 1, abort_flag)) return -1;
+  const int t = *reinterpret_cast<volatile int*>(&q->ring[slot]);
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(&q->freed[slot]);
+  return t;
+}
+// Fetcher side (lane 0 of ONE warp of the CTA).  The index for tile k+1 is drawn (tile_queue_draw: one atomicAdd,
+// result not consumed) when the fetcher starts working on tile k and published when it is done with it, so the two L2
+// round trips (counter, order table) are off the critical path.
+// The first tile of every CTA is its block index (no atomic: hundreds of CTAs hitting one address at launch serialise in
+// the L2 atomic unit, ~4 us measured); later tiles are gridDim.x + a draw from the counter.
+// counter == nullptr (BSMM_STATIC_TILES=1): the round-1 static deal, tile k of a CTA = blockIdx.x + k * gridDim.x.
+__device__ __forceinline__ int tile_queue_draw(int* counter, uint32_t k_next) {
+  return counter ? (int)gridDim.x + atomicAdd(counter, 1) : (int)(blockIdx.x + k_next * gridDim.x);
+}
+__device__ __forceinline__ void tile_queue_publish(TileQueue* q, uint32_t k, int drawn, const int32_t* order, int total, volatile int* abort_flag) {
+  const uint32_t slot = k % TILE_RING;
+  bool ok = true;
+  if (k >= TILE_RING) ok = ptx::mbar_wait(&q->freed[slot], ((k / TILE_RING) - 1) & 1, abort_flag);   // every warp has read the slot's previous tile
+  int t = -1;
+  if (ok && drawn < total) t = order ? order[drawn] : drawn;
+  q->ring[slot] = t;
+  ptx::mbar_arrive(&q->ready[slot]);
+}
+// last CTA out resets the counter pair for its next user
+__device__ __forceinline__ void tile_queue_retire(int* counter) {
+  __threadfence();
+  if (atomicAdd(counter + 1, 1) == (int)gridDim.x - 1) { counter[0] = 0; counter[1] = 0; __threadfence(); }
+}
+
 struct XpropTcParams {
   const int32_t* sched;      // tile schedule (lut.py:build_tile_schedule)
   int groups_off;            // int32 index of the first group record
@@ -144,6 +214,8 @@ struct XpropTcParams {
   void* y;                   // output base, row pitch and row count (direct-store epilogue)
   long long y_pitch;         // elements
   int N;
+  int* counter;              // tile queue: {next index, CTAs retired}
+  const int32_t* order;      // tile order (heaviest first) or nullptr = natural order
 };
 struct XpropTmaps { CUtensorMap x, w, y; };
 
@@ -169,6 +241,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   __shared__ __align__(16) int4 cmd[XS][8];       // per run: (B descriptor low word for K slice 0, D tmem address, idesc, accumulate)
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
+  __shared__ TileQueue tq;
   volatile int* abort_flag = &abort_s;
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -177,6 +250,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
 
   if (tid == 0) {
     abort_s = 0;
+    tile_queue_init(&tq, (int)(blockDim.x / 32));
     for (int i = 0; i < XS; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     ptx::mbar_init(&acc_full, NP);
     ptx::mbar_init(&acc_empty, 1);
@@ -200,7 +274,13 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full[0])), empty0 = ptx::opaque(ptx::smem_u32(&empty[0])),
                    cmd0 = ptx::opaque(ptx::smem_u32(&cmd[0][0])), stage0 = ptx::opaque(ptx::smem_u32(sStage));
     const uint32_t p_bdesc_lo = (uint32_t)ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
-    for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x) {
+    const bool fetcher = warp == 0 && lane == 0;
+    int drawn = 0;
+    if (fetcher) tile_queue_publish(&tq, 0, (int)blockIdx.x, p.order, total_tiles, abort_flag);
+    for (uint32_t tk = 0; alive; ++tk) {
+      const int t = tile_queue_next(&tq, tk, lane, abort_flag);
+      if (t < 0) break;
+      if (fetcher) drawn = tile_queue_draw(p.counter, tk + 1);            // for tile tk + 1; consumed after this tile's loads are issued
       const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
       const int32_t* th = sched + 4 + 4 * kt;
       const int first_group = th[0], n_groups = th[1];
@@ -246,6 +326,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         __syncwarp();
       }
       gbase += n_groups;
+      if (fetcher && alive) tile_queue_publish(&tq, tk + 1, drawn, p.order, total_tiles, abort_flag);
     }
   } else if (warp < 2 * NP) {
     // ================================ MMA issuers ================================
@@ -269,7 +350,9 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     uint32_t tile_it = 0, gbase = 0;
     const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
     bool alive = true;
-    for (int t = blockIdx.x; t < total_tiles && alive; t += gridDim.x, ++tile_it) {
+    for (; alive; ++tile_it) {
+      const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
+      if (t < 0) break;
       const int kt = t % p.n_ktiles;
       const int n_groups = sched[4 + 4 * kt + 1];
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, tile_it & 1, abort_flag))) { g_tc_error = 3; break; }
@@ -339,7 +422,9 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     ptx::tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (etid == 0) ptx::mbar_arrive(&acc_empty);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+    for (;; ++tile_it) {
+      const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
+      if (t < 0) break;
       const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
       const int32_t* th = sched + 4 + 4 * kt;
       const int first_out = th[2];
@@ -468,6 +553,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == NP) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
+  if (tid == 0 && p.counter) tile_queue_retire(p.counter);
 }
 
 template <int BS, int OCC, int VAR = 0>
@@ -490,13 +576,15 @@ int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count
 
 inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lut, int n_out, int n_in, int blocks,
                     const void* x, const void* w, void* y, int N, const float* gate, const int32_t* sched, int sched_tiles, int sched_tile_blocks,
-                    int sched_groups_off, cudaStream_t s) {
+                    int sched_groups_off, int order_off, int order_ntiles, cudaStream_t s) {
   (void)lut;
   if (dtype != BSMM_F16 && dtype != BSMM_BF16) { fail(0, "fp32 runs on the FMA path"); return TC_NOT_APPLICABLE; }
   if (bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
   if (gate != nullptr) { fail(0, "gated xprop uses the CUDA-core path"); return TC_NOT_APPLICABLE; }
   if (axis == 0 && (N & 7)) { fail(0, "feature_axis 0 needs N %% 8 == 0 for TMA (row pitch multiple of 16 bytes)"); return TC_NOT_APPLICABLE; }
   if (sched == nullptr || sched_tiles <= 0) { fail(0, "no tile schedule supplied"); return TC_NOT_APPLICABLE; }
+  if (order_off > 0 && order_ntiles != (N + 127) / 128)
+    return fail(BSMM_E_ARG, "bsmm_xprop: tile order built for %d minibatch tiles, N=%d needs %d", order_ntiles, N, (N + 127) / 128);
   if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) { fail(0, "pointers must be 16-byte aligned for TMA"); return TC_NOT_APPLICABLE; }
   const DeviceInfo& dev = device_info();
   if (!dev.ok || dev.cc_major != 10) { fail(0, "tcgen05 needs an sm_100 device"); return TC_NOT_APPLICABLE; }
@@ -525,6 +613,9 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   // the schedule itself lives in device memory; its shape is passed by value
   p.n_ktiles = sched_tiles;
   p.groups_off = sched_groups_off;
+  p.counter = static_tiles() ? nullptr : next_tile_counter();
+  if (!p.counter && !static_tiles()) return fail(BSMM_E_NODEV, "bsmm_xprop: tile counters not available");
+  p.order = (order_off > 0 && !static_order()) ? sched + order_off : nullptr;
   const int tile_blocks = sched_tile_blocks & 0xff;
   const int w_per_group = sched_tile_blocks >> 8;          // 0 = the default of the tile width
   const int occ = (tile_blocks * bsize <= 256) ? 2 : 1;      // half-width tiles run two CTAs per SM

@@ -38,6 +38,7 @@ struct UpdatTcParams {
   const float* gate;        // optional, only with gated
   int gated;
   void* dw;
+  int* counter;             // tile queue (csrc/tc.cuh): tiles are already sorted heaviest first by the schedule
 };
 struct UpdatTmaps { CUtensorMap x[BSMM_MAX_PAIRS]; CUtensorMap dy[BSMM_MAX_PAIRS]; };
 
@@ -58,6 +59,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
   __shared__ uint64_t full[ST], empty[ST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
+  __shared__ TileQueue tq;
   volatile int* abort_flag = &abort_s;
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -67,6 +69,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
 
   if (tid == 0) {
     abort_s = 0;
+    tile_queue_init(&tq, UPDAT_THREADS / 32);
     for (int i = 0; i < ST; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 1); }
     ptx::fence_mbar_init();
@@ -81,7 +84,13 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
     // ================================ TMA producers ================================
     uint32_t sbase = 0;                     // stages of earlier tiles
     bool alive = true;
-    for (int t = blockIdx.x; t < p.n_tiles && alive; t += gridDim.x) {
+    const bool fetcher = warp == 0 && lane == 0;
+    int drawn = 0;
+    if (fetcher) tile_queue_publish(&tq, 0, (int)blockIdx.x, nullptr, p.n_tiles, abort_flag);
+    for (uint32_t tk = 0; alive; ++tk) {
+      const int t = tile_queue_next(&tq, tk, lane, abort_flag);
+      if (t < 0) break;
+      if (fetcher) drawn = tile_queue_draw(p.counter, tk + 1);
       const int32_t* rec = recs + (size_t)t * 64;
       const int c0 = rec[0], n_act = rec[1];
       const int my_k = (lane >= 2 && lane < 2 + n_act) ? rec[8 + lane - 2] : 0;
@@ -109,6 +118,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
         __syncwarp();
       }
       sbase += n_chunks;
+      if (fetcher && alive) tile_queue_publish(&tq, tk + 1, drawn, nullptr, p.n_tiles, abort_flag);
     }
   } else if (warp == 2) {
     // ================================ MMA issuer ================================
@@ -122,7 +132,9 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
     const uint32_t b_kstep16 = p.axis0 ? 2u : (B_KSTEP >> 4);
     uint32_t sc = 0, tile_it = 0;
     bool alive = true;
-    for (int t = blockIdx.x; t < p.n_tiles && alive; t += gridDim.x, ++tile_it) {
+    for (; alive; ++tile_it) {
+      const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
+      if (t < 0) break;
       const int n_act = recs[(size_t)t * 64 + 1];
       const uint32_t buf = tile_it & 1;
       const uint32_t idesc = ptx::make_idesc_f16(BF16, !p.axis0, !p.axis0, 128, n_act * BS);
@@ -154,7 +166,9 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
     const int row = (quad * 32) % BS + lane;            // row inside the BS x BS block
     TO* dw = reinterpret_cast<TO*>(p.dw);
     uint32_t tile_it = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++tile_it) {
+    for (;; ++tile_it) {
+      const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
+      if (t < 0) break;
       const int32_t* rec = recs + (size_t)t * 64;
       const int n_act = rec[1];
       const uint32_t buf = tile_it & 1;
@@ -222,6 +236,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+  if (tid == 0 && p.counter) tile_queue_retire(p.counter);
 }
 
 template <int BS>
@@ -276,6 +291,8 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   p.axis0 = axis == 0;
   p.sched = sched; p.n_tiles = sched_tiles; p.k_per_tile = sched_tile_blocks; p.N = N; p.pcount = pcount;
   p.alpha = alpha; p.beta = beta; p.gate = gate; p.gated = (gated_dw && gate) ? 1 : 0; p.dw = dw;
+  p.counter = static_tiles() ? nullptr : next_tile_counter();
+  if (!p.counter && !static_tiles()) return fail(BSMM_E_NODEV, "bsmm_updat: tile counters not available");
   const bool bf = dtype == BSMM_BF16;
   const bool f32out = dw_dtype == BSMM_F32;
   if (bsize == 32) {

@@ -54,6 +54,8 @@ def reserve_sms_for_nccl(n_sms=8, nccl_ctas=None):
     margin = int(os.environ["BSMM_SM_MARGIN"])
     if margin > 0:
         os.environ.setdefault("NCCL_MAX_CTAS", str(int(nccl_ctas or margin)))
+        # (BSMM_TILE_QUEUE=dynamic lets late-starting CTAs pull tiles from a global counter instead of owning a fixed
+        # share; with a margin that NCCL respects it measured the same as the static deal, profiles/r2_scaling.txt)
     return margin
 
 

@@ -171,10 +171,10 @@ class MatmulLuts(object):
         n_out = self.CB if bprop else self.KB
         return build_pair_schedule(outs, ins, wids, n_out, blocks_per_tile, w_per_group, n_tiles, n_ntiles, n_ctas, bsize)
 
-    def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None):
+    def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None, n_ntiles=None):
         outs, ins, wids = self._b if bprop else self._f
         n_out = self.CB if bprop else self.KB
-        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group, n_tiles)
+        return build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group, n_tiles, n_ntiles)
 
 
 GROUP_INTS = 32          # one 128-byte record per schedule group (one coalesced warp load)
@@ -203,7 +203,22 @@ def pick_tile_count(n_out, n_ntiles, cta_slots, max_blocks_per_tile):
     return best[1]
 
 
-def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None):
+def tile_order(tile_cost, n_ntiles):
+    """Order in which the persistent CTAs pull the n_ntiles x len(tile_cost) tiles from the global counter: heaviest
+    output tiles first (greedy longest-processing-time, so a skewed layout's few heavy tiles do not end up as the tail),
+    costs bucketed to 12.5 % so that a uniform layout keeps the natural order (all output tiles of one minibatch tile
+    back to back: its activation panel stays hot).  int32 [n_ntiles * n_ktiles] of tile ids nt * n_ktiles + kt."""
+    cost = np.asarray(tile_cost, dtype=np.float64)
+    n_kt = len(cost)
+    top = cost.max() if n_kt and cost.max() > 0 else 1.0
+    bucket = np.floor(8.0 * cost / top).astype(np.int64)
+    kt = np.tile(np.arange(n_kt), n_ntiles)
+    nt = np.repeat(np.arange(n_ntiles), n_kt)
+    order = np.lexsort((kt, nt, -bucket[kt]))
+    return (nt[order] * n_kt + kt[order]).astype(np.int32)
+
+
+def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None, n_ntiles=None):
     """Schedule for the tcgen05 xprop kernel (csrc/tc.cuh).
 
     An output tile covers `blocks_per_tile` consecutive output blocks (their fp32 accumulators live
@@ -300,6 +315,13 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
     r1 = (((run_len * bsize) >> 3) << 17) | accumulate[run_first]
     gr[run_group, 12 + run_pos] = r0
     gr[run_group, 20 + run_pos] = r1
+    if n_ntiles is not None:
+        # tile order table for the dynamic tile queue (csrc/tc.cuh): cost ~ activation tiles staged + W blocks multiplied
+        w_per_tile = np.bincount(tile, minlength=n_tiles) if nnz else np.zeros(n_tiles, dtype=np.int64)
+        cost = 4.0 * groups_per_tile + 1.0 * w_per_tile + 4.0
+        order = tile_order(cost, int(n_ntiles))
+        order_off = len(sched)
+        return np.concatenate((sched, order)), grp_off, order_off
     return sched, grp_off
 
 

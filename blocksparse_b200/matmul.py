@@ -190,7 +190,7 @@ class BlocksparseMatMul(object):
                 arr, off, loff = self._luts.pair_schedule(bprop, tb, wps, n_kt, n_nt, n_ctas)
                 while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:
                     d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
-                plan = d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), n_kt, off, loff, n_ctas, n_nt, tb | (variant << 8))
+                plan = d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), n_kt, off, loff, n_ctas, n_nt, tb | (variant << 8) | (1 << 16))
             sched, sched_tiles, sched_off, list_off, n_ctas, n_nt, tile_arg = plan
         elif "xprop_sched" in d:
             # tile count chosen so that (minibatch tiles) x (feature tiles) fills whole waves of the persistent grid
@@ -206,13 +206,14 @@ class BlocksparseMatMul(object):
             elif _OCC[32] == 2 and self.bsize == 32 and self.blocks * tb <= 3.0 * self.CB * self.KB:
                 # 1..3 W blocks per group on average (density <= 37.5 %): 4 W slots per stage, 6 stages in flight
                 wpg, sparse = 4, True
-            key = (bool(bprop), n_kt, wpg)
+            n_nt = -(-N // 128)
+            key = (bool(bprop), n_kt, wpg, n_nt)
             if key not in d["xprop_sched"]:
-                arr, off = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt)
-                while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:       # bounded: one entry per distinct tile count
+                arr, off, ooff = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt, n_ntiles=n_nt)
+                while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:       # bounded: one entry per distinct minibatch tile count
                     d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
-                d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off)
-            sched, sched_tiles, sched_off = d["xprop_sched"][key]
+                d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off, ooff)
+            sched, sched_tiles, sched_off, list_off = d["xprop_sched"][key]
             tile_arg = tb | ((wpg << 8) if sparse else 0)
         y2 = torch.empty((feat_out, N) if self.axis == 0 else (N, feat_out), dtype=x.dtype, device=x.device)
         if gate is not None:

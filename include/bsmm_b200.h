@@ -105,9 +105,11 @@ int         bsmm_debug_trace(unsigned long long* out, int n);
  *    per schedule group when it differs from the default: 2 or 4 select the deeper-pipeline variants used for
  *    layouts below ~12 % / ~37 % density), group records starting at int32 index sched_groups_off; NULL selects
  *    the CUDA-core kernels.
- *    Pair schedule (32 x 32 blocks, lut.py:build_pair_schedule): sched_list_off > 0 gives the int32 index of the
- *    per-CTA tile lists that follow the group records (built for sched_ctas CTAs and sched_ntiles = ceil(N/128)
- *    minibatch tiles) and bits 8.. of sched_tile_blocks select the kernel variant (1 sparse, 2 mid, 3 wide tiles).
+ *    The persistent CTAs pull tiles from a global counter; sched_list_off > 0 gives the int32 index (inside sched) of an
+ *    optional tile ORDER table (tile ids, heaviest first, built for sched_ntiles = ceil(N/128) minibatch tiles).
+ *    Pair schedule (32 x 32 blocks, lut.py:build_pair_schedule, opt-in): bit 16 of sched_tile_blocks set; then
+ *    sched_list_off indexes the per-CTA tile lists (built for sched_ctas CTAs and sched_ntiles minibatch tiles) and
+ *    bits 8..15 select the kernel variant (1 sparse, 2 mid, 3 wide tiles).
  * gate: optional float[blocks]; a zero gate skips the block (cn_64.cu:96-98).  With a gate the call runs on the
  *    CUDA-core kernels; for 16-bit weights call bsmm_gate_weights first and pass gate = NULL to stay on tcgen05.
  */
