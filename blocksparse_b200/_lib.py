@@ -35,6 +35,16 @@ SIGNATURES = {
     "bst_softmax": (_i, [_i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
     "bst_softmax_grad": (_i, [_i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
     "bst_autoregressive_mask": (_i, [_i, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "bsmm_block_norm": (_i, [_i, _i, _i, _vp, _vp, _i, _vp]),
+    "bsmm_l2_decay": (_i, [_i, _i, _i, _vp, _vp, _f, _f, _vp]),
+    "bsmm_threshold_prune": (_i, [_i, _i, _i, _vp, _vp, _f, _i, _vp]),
+    "bsmm_prune_topk": (_i, [_vp, _vp, _i, _i, _vp]),
+    "bsmm_identity_init": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _f, _vp]),
+    "bsmm_l2_normalize": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp]),
+    "bsmm_l2_normalize_grad": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
+    "bsmm_reduced_dw_workspace_bytes": (_c.c_size_t, [_i, _i]),
+    "bsmm_reduced_dw": (_i, [_i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "bsmm_gather_rows": (_i, [_i, _vp, _vp, _vp, _vp, _i, _c.c_longlong, _i, _vp]),
     "bsmm_timer_create": (_i, [_c.POINTER(_vp)]),
     "bsmm_timer_begin": (_i, [_vp, _vp]),
     "bsmm_timer_end": (_i, [_vp, _vp, _c.POINTER(_f)]),

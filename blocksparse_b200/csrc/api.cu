@@ -4,6 +4,7 @@
 #include "generic.cuh"
 #include "softmax.cuh"
 #include "tc.cuh"
+#include "wutil.cuh"
 
 using namespace bsmm;
 
@@ -357,4 +358,124 @@ int bsmm_timer_destroy(void* timer) {
   return 0;
 }
 
+
+// ---- weight utilities (csrc/wutil.cuh) ---------------------------------------------------------------------------
+static int check_blocks(const char* what, int bsize, int blocks, const void* p) {
+  if (!p || blocks <= 0) return fail(BSMM_E_ARG, "%s: bad arguments", what);
+  return check_bsize_axis(bsize, 0);
+}
+
+int bsmm_block_norm(int dtype, int bsize, int blocks, const void* w, float* norm, int norm_type, void* stream) {
+  if (int e = check_blocks("bsmm_block_norm", bsize, blocks, w)) return e;
+  if (!norm) return fail(BSMM_E_ARG, "bsmm_block_norm: null output");
+  const int wpb = 4;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    block_norm_kernel<T><<<(blocks + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>((const T*)w, norm, blocks, bsize * bsize, norm_type != 0);
+  });
+  return check_launch("block_norm");
+}
+
+int bsmm_l2_decay(int dtype, int bsize, int blocks, void* w, const float* gate, float rate, float epsilon, void* stream) {
+  if (int e = check_blocks("bsmm_l2_decay", bsize, blocks, w)) return e;
+  const int wpb = 4;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    l2_decay_kernel<T><<<(blocks + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>((T*)w, gate, blocks, bsize * bsize, rate, epsilon);
+  });
+  return check_launch("l2_decay");
+}
+
+int bsmm_threshold_prune(int dtype, int bsize, int blocks, const void* w, float* gate, float threshold, int norm_type, void* stream) {
+  if (int e = check_blocks("bsmm_threshold_prune", bsize, blocks, w)) return e;
+  if (!gate) return fail(BSMM_E_ARG, "bsmm_threshold_prune: null gate");
+  const int wpb = 4;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    threshold_prune_kernel<T><<<(blocks + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>((const T*)w, gate, blocks, bsize * bsize, threshold, norm_type != 0);
+  });
+  return check_launch("threshold_prune");
+}
+
+int bsmm_prune_topk(float* gate, const int32_t* idx, int blocks, int keep, void* stream) {
+  if (!gate || !idx || blocks <= 0 || keep < 0) return fail(BSMM_E_ARG, "bsmm_prune_topk: bad arguments");
+  prune_topk_kernel<<<(blocks + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gate, idx, blocks, keep);
+  return check_launch("prune_topk");
+}
+
+int bsmm_identity_init(int dtype, int bsize, int blocks, const int32_t* updat_lut, int n_c_blocks, int n_k_blocks, void* w, float scale, void* stream) {
+  if (int e = check_blocks("bsmm_identity_init", bsize, blocks, w)) return e;
+  if (!updat_lut || n_c_blocks <= 0 || n_k_blocks <= 0) return fail(BSMM_E_ARG, "bsmm_identity_init: bad arguments");
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    identity_init_kernel<T><<<blocks, 128, 0, (cudaStream_t)stream>>>((T*)w, updat_lut, blocks, bsize, n_c_blocks, n_k_blocks, scale);
+  });
+  return check_launch("identity_init");
+}
+
+int bsmm_l2_normalize(int dtype, int y_dtype, int bsize, const int32_t* lut, int n_out, const void* w, const float* gain, void* y,
+                      float* sum_sqr, float epsilon, void* stream) {
+  if (int e = check_bsize_axis(bsize, 0)) return e;
+  if (!lut || !w || !y || !sum_sqr || n_out <= 0) return fail(BSMM_E_ARG, "bsmm_l2_normalize: bad arguments");
+  if (y_dtype != dtype && y_dtype != BSMM_F32) return fail(BSMM_E_DTYPE, "bsmm_l2_normalize: output dtype must be fp32 or the input dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    if (y_dtype == BSMM_F32) l2_normalize_kernel<T, float><<<n_out, L2N_THREADS, 0, s>>>((const T*)w, gain, (float*)y, sum_sqr, lut, bsize, epsilon);
+    else                     l2_normalize_kernel<T, T><<<n_out, L2N_THREADS, 0, s>>>((const T*)w, gain, (T*)y, sum_sqr, lut, bsize, epsilon);
+  });
+  return check_launch("l2_normalize");
+}
+
+int bsmm_l2_normalize_grad(int dtype, int y_dtype, int bsize, const int32_t* lut, int n_out, const void* dy, const void* w, const float* gain,
+                           const float* sum_sqr, void* dx, float* dg, float epsilon, void* stream) {
+  if (int e = check_bsize_axis(bsize, 0)) return e;
+  if (!lut || !dy || !w || !sum_sqr || !dx || n_out <= 0) return fail(BSMM_E_ARG, "bsmm_l2_normalize_grad: bad arguments");
+  if (y_dtype != dtype && y_dtype != BSMM_F32) return fail(BSMM_E_DTYPE, "bsmm_l2_normalize_grad: dy dtype must be fp32 or the weight dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    if (y_dtype == BSMM_F32) l2_normalize_grad_kernel<T, float><<<n_out, L2N_THREADS, 0, s>>>((const float*)dy, (const T*)w, gain, sum_sqr, (T*)dx, dg, lut, bsize, epsilon);
+    else                     l2_normalize_grad_kernel<T, T><<<n_out, L2N_THREADS, 0, s>>>((const T*)dy, (const T*)w, gain, sum_sqr, (T*)dx, dg, lut, bsize, epsilon);
+  });
+  return check_launch("l2_normalize_grad");
+}
+
+size_t bsmm_reduced_dw_workspace_bytes(int n_c_blocks, int n_k_blocks) { return (size_t)8 * n_c_blocks * n_k_blocks * sizeof(float); }
+
+int bsmm_reduced_dw(int dtype, int axis, int bsize, const void* const* xs, const void* const* dys, int pcount,
+                    int n_c_blocks, int n_k_blocks, int N, float scale, int norm_type, float* dw, int accumulate,
+                    void* x_red, void* y_red, void* workspace, void* stream) {
+  if (int e = check_bsize_axis(bsize, axis)) return e;
+  if (!xs || !dys || !dw || !x_red || !y_red || !workspace) return fail(BSMM_E_ARG, "bsmm_reduced_dw: null pointer");
+  if (pcount < 1 || pcount > BSMM_MAX_PAIRS || n_c_blocks <= 0 || n_k_blocks <= 0 || N <= 0) return fail(BSMM_E_ARG, "bsmm_reduced_dw: bad sizes");
+  if (dtype == BSMM_F32) return fail(BSMM_E_DTYPE, "bsmm_reduced_dw: 16-bit activations only (reference: half)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int l2 = norm_type != 0;
+  const int splits = 8;
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    if (scale != 0.0f) {        // a zero scale skips the reductions (reference op.cc:754-766)
+      for (int p = 0; p < pcount; ++p) {
+        if (!xs[p] || !dys[p]) return fail(BSMM_E_ARG, "bsmm_reduced_dw: null pointer in pair %d", p);
+        const long long tx = (long long)n_c_blocks * N, ty = (long long)n_k_blocks * N;
+        feature_reduce_kernel<T><<<(unsigned)((tx + 255) / 256), 256, 0, s>>>((const T*)xs[p], (T*)x_red, axis, bsize, n_c_blocks, N, p, pcount, l2);
+        feature_reduce_kernel<T><<<(unsigned)((ty + 255) / 256), 256, 0, s>>>((const T*)dys[p], (T*)y_red, axis, bsize, n_k_blocks, N, p, pcount, l2);
+      }
+    }
+    const long long R = (long long)pcount * N;
+    dim3 grid((n_c_blocks + 15) / 16, (n_k_blocks + 15) / 16, splits);
+    if (axis == 1)     // (pair, n, block): row r = pair*N + n, block contiguous
+      reduced_gemm_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x_red, (const T*)y_red, (float*)workspace, n_c_blocks, n_k_blocks, R,
+                                                          n_c_blocks, 1, n_k_blocks, 1, splits);
+    else               // (block, pair, n): row r = pair*N + n contiguous, block stride R
+      reduced_gemm_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x_red, (const T*)y_red, (float*)workspace, n_c_blocks, n_k_blocks, R,
+                                                          1, R, 1, R, splits);
+  });
+  const int total = n_c_blocks * n_k_blocks;
+  reduced_gemm_finish_kernel<<<(total + 255) / 256, 256, 0, s>>>((const float*)workspace, dw, total, splits, scale, accumulate);
+  return check_launch("reduced_dw");
+}
+
+int bsmm_gather_rows(int dtype, const void* x, const void* y, const int32_t* idx, void* out, int rows, long long N, int op, void* stream) {
+  if (!x || !idx || !out || rows <= 0 || N <= 0 || op < 0 || op > 2 || (op != 0 && !y)) return fail(BSMM_E_ARG, "bsmm_gather_rows: bad arguments");
+  const unsigned gx = (unsigned)((N + 255) / 256 > 64 ? 64 : (N + 255) / 256);
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    gather_rows_kernel<T><<<dim3(gx, rows), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, idx, (T*)out, rows, N, op);
+  });
+  return check_launch("gather_rows");
+}
 }  // extern "C"

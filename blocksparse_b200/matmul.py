@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .checkers import MatmulCheckers
 from .lut import MatmulLuts, pick_tile_count
 
 # Output blocks per xprop tile and CTAs per SM (csrc/tc.cuh XpropCfg<BS, OCC>), picked from B200 timings
@@ -43,7 +44,7 @@ def _as_2d(t, axis, feat):
     return t.reshape(-1, feat)
 
 
-class BlocksparseMatMul(object):
+class BlocksparseMatMul(MatmulCheckers):
     """Drop-in for blocksparse.matmul.BlocksparseMatMul (reference matmul.py:74).
 
     layout        : 2-D 0/1 array (CB, KB) of active blocks
@@ -92,13 +93,51 @@ class BlocksparseMatMul(object):
 
     # ------------------------------------------------------------------ initialisers
     def identity_init(self, scale=1.0, dtype=torch.float32, device="cuda"):
-        """W such that blocks on the (wrapped) diagonal are scale*I (matmul.py:317-329)."""
-        W = torch.zeros(self.w_shape, dtype=dtype, device=device)
-        cs, ks = self.updat_lut[:, 0], self.updat_lut[:, 1]
-        diag = np.nonzero((cs % self.KB) == (ks % self.CB))[0]
-        if len(diag):
-            W[torch.as_tensor(diag, device=device)] = scale * torch.eye(self.bsize, dtype=dtype, device=device)
+        """W such that blocks on the (wrapped) diagonal are scale*I (matmul.py:317-329, IdentityInitCK kernel)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.BsmmError("identity_init runs on the GPU (no CPU path)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        W = torch.empty(self.w_shape, dtype=dtype, device=device)
+        d = self._device_luts(device)
+        with torch.cuda.device(device):
+            rc = _lib.load().bsmm_identity_init(_lib.dtype_code(dtype), self.bsize, self.blocks, d["updat"].data_ptr(), self.CB, self.KB,
+                                                W.data_ptr(), float(scale), _lib.stream_ptr())
+        _lib.check(rc, "bsmm_identity_init")
         return W
+
+    def ortho_init(self, dtype=torch.float32, device="cuda", rng=None):
+        """Orthogonal columns inside every output block column (sparse layouts) or a dense orthogonal matrix cut into
+        blocks (fully dense layouts) -- matmul.py:292-322; host-side SVD, one-off."""
+        rng = rng or np.random
+        bs = self.bsize
+        W = np.empty(self.w_shape, dtype=np.float32)
+        if self.sparsity < 1.0:
+            for k, col in self.fprop_list:
+                if not col:
+                    continue
+                shape = (len(col) * bs, bs)
+                a = rng.normal(0.0, 1.0, shape).astype(np.float32)
+                u, _, v = np.linalg.svd(a, full_matrices=False)
+                if u.shape != shape:
+                    u = v
+                for i, (c, w) in enumerate(col):
+                    W[w] = u[i * bs:(i + 1) * bs, :]
+        else:
+            shape = (self.C, self.K)
+            a = rng.normal(0.0, 1.0, shape).astype(np.float32)
+            u, _, v = np.linalg.svd(a, full_matrices=False)
+            if u.shape != shape:
+                u = v
+            for w, (c, k) in enumerate(self.updat_list):
+                W[w] = u[c * bs:(c + 1) * bs, k * bs:(k + 1) * bs]
+        return torch.as_tensor(W).to(dtype).to(device)
+
+    def l2_normalize(self, W, gain=None, epsilon=1e-12, dtype=None):
+        """y = gain * W / sqrt(max(sum(W^2), eps)), the sum taken per OUTPUT feature over its whole sparse column
+        (matmul.py:445-453); differentiable in W and gain.  dtype: output dtype (default W's; fp32 allowed)."""
+        return _L2NormalizeFunction.apply(W, gain, self, float(epsilon), dtype or W.dtype)
 
     def checker_init(self, dtype=torch.float32, device="cuda"):
         """Checkerboard gate (matmul.py:331-337)."""
@@ -428,3 +467,207 @@ class group_param_grads(object):
                 g = self.pending.dw.to(self.w.dtype)
                 self.w.grad = g if self.w.grad is None else self.w.grad + g
         return False
+
+
+class _L2NormalizeFunction(torch.autograd.Function):
+    """L2NormalizeCK / L2NormalizeGainCK and their gradients (reference matmul.py:530-551)."""
+
+    @staticmethod
+    def forward(ctx, W, gain, bsmm, epsilon, out_dtype):
+        if not W.is_cuda:
+            raise _lib.BsmmError("l2_normalize needs CUDA tensors (no CPU path)")
+        if tuple(W.shape) != bsmm.w_shape:
+            raise ValueError("W must have shape %s" % (bsmm.w_shape,))
+        W = W.contiguous()
+        g = None if gain is None else gain.to(torch.float32).contiguous()
+        if g is not None and g.numel() != bsmm.K:
+            raise ValueError("gain must have K = %d entries" % bsmm.K)
+        y = torch.empty(bsmm.w_shape, dtype=out_dtype, device=W.device)
+        ss = torch.empty(bsmm.K, dtype=torch.float32, device=W.device)
+        d = bsmm._device_luts(W.device)
+        with torch.cuda.device(W.device):
+            rc = _lib.load().bsmm_l2_normalize(_lib.dtype_code(W.dtype), _lib.dtype_code(out_dtype), bsmm.bsize, d["fprop"].data_ptr(),
+                                               bsmm.KB, W.data_ptr(), _lib.ptr(g), y.data_ptr(), ss.data_ptr(), epsilon, _lib.stream_ptr())
+        _lib.check(rc, "bsmm_l2_normalize")
+        ctx.bsmm, ctx.epsilon, ctx.has_gain, ctx.gain_dtype = bsmm, epsilon, gain is not None, None if gain is None else gain.dtype
+        ctx.save_for_backward(W, g, ss)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        W, g, ss = ctx.saved_tensors
+        bsmm = ctx.bsmm
+        dy = dy.contiguous()
+        if dy.dtype not in (W.dtype, torch.float32):
+            dy = dy.to(W.dtype)
+        dx = torch.empty_like(W)
+        dg = torch.empty(bsmm.K, dtype=torch.float32, device=W.device) if ctx.has_gain else None
+        d = bsmm._device_luts(W.device)
+        with torch.cuda.device(W.device):
+            rc = _lib.load().bsmm_l2_normalize_grad(_lib.dtype_code(W.dtype), _lib.dtype_code(dy.dtype), bsmm.bsize, d["fprop"].data_ptr(),
+                                                    bsmm.KB, dy.data_ptr(), W.data_ptr(), _lib.ptr(g), ss.data_ptr(), dx.data_ptr(),
+                                                    _lib.ptr(dg), ctx.epsilon, _lib.stream_ptr())
+        _lib.check(rc, "bsmm_l2_normalize_grad")
+        return dx, (dg.to(ctx.gain_dtype).view(-1) if dg is not None else None), None, None, None
+
+
+def blocksparse_reduced_dw(xs, dys, scale, dwi=None, bsize=32, norm="max", axis=0):
+    """Block-reduced FULL weight gradient for network growth (BlocksparseReducedDW, reference matmul.py:556-609,
+    src/blocksparse_matmul_op.cc:639-773): every activation / gradient tensor is reduced over the bsize features of each
+    block (max|.| or l2 norm), then dw[bC, bK] = scale * sum over pairs and minibatch of x_red * y_red (+ dwi, in place).
+
+    xs, dys: lists of up to 8 16-bit tensors, (C, N) for axis 0 or (N, C) for axis 1.  Returns (dw fp32, x_red, y_red).
+    """
+    if torch.is_tensor(xs):
+        xs, dys = [xs], [dys]
+    if len(xs) != len(dys) or not 1 <= len(xs) <= _lib.MAX_PAIRS:
+        raise ValueError("need 1..%d (x, dy) pairs" % _lib.MAX_PAIRS)
+    x0 = xs[0]
+    if not x0.is_cuda:
+        raise _lib.BsmmError("blocksparse_reduced_dw needs CUDA tensors (no CPU path)")
+    xs = [x.reshape(x.shape[0], -1).contiguous() if axis == 0 else x.reshape(-1, x.shape[-1]).contiguous() for x in xs]
+    dys = [e.reshape(e.shape[0], -1).contiguous() if axis == 0 else e.reshape(-1, e.shape[-1]).contiguous() for e in dys]
+    C, K = xs[0].shape[axis], dys[0].shape[axis]
+    N = xs[0].shape[1 - axis]
+    if C % bsize or K % bsize:
+        raise ValueError("feature dims must be multiples of the block size")
+    bC, bK, P = C // bsize, K // bsize, len(xs)
+    for a, b in zip(xs, dys):
+        if a.dtype != x0.dtype or b.dtype != x0.dtype or a.shape[1 - axis] != N or b.shape[1 - axis] != N or a.shape[axis] != C or b.shape[axis] != K:
+            raise ValueError("all pairs must share dtype, minibatch and feature sizes")
+    dev = x0.device
+    x_red = torch.empty((bC, P, N) if axis == 0 else (P, N, bC), dtype=x0.dtype, device=dev)
+    y_red = torch.empty((bK, P, N) if axis == 0 else (P, N, bK), dtype=x0.dtype, device=dev)
+    if dwi is None:
+        dw, acc = torch.empty((bC, bK), dtype=torch.float32, device=dev), 0
+    else:
+        if tuple(dwi.shape) != (bC, bK) or dwi.dtype != torch.float32 or not dwi.is_contiguous():
+            raise ValueError("dwi must be a contiguous float32 (%d, %d) tensor" % (bC, bK))
+        dw, acc = dwi, 1
+    lib = _lib.load()
+    ws = torch.empty(lib.bsmm_reduced_dw_workspace_bytes(bC, bK), dtype=torch.uint8, device=dev)
+    arr_t = ctypes.c_void_p * P
+    with torch.cuda.device(dev):
+        rc = lib.bsmm_reduced_dw(_lib.dtype_code(x0.dtype), axis, bsize, arr_t(*[t.data_ptr() for t in xs]), arr_t(*[t.data_ptr() for t in dys]),
+                                 P, bC, bK, N, float(scale), 0 if norm.lower() == "max" else 1, dw.data_ptr(), acc,
+                                 x_red.data_ptr(), y_red.data_ptr(), ws.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "bsmm_reduced_dw")
+    return dw, x_red, y_red
+
+
+def block_reduced_full_dw(pairs, scale=1.0, norm="max", group_size=8, bsize=32, axis=0):
+    """Eager counterpart of the reference's graph rewrite (matmul.py:556-609): `pairs` is the list of (x, dy) tensors of
+    every use of a shared weight (what the rewrite collects from the BlocksparseMatmulDW ops); they are reduced
+    `group_size` (<= 8) at a time, accumulating into one (bC, bK) fp32 tensor."""
+    assert 1 <= group_size <= _lib.MAX_PAIRS
+    dw = None
+    for off in range(0, len(pairs), group_size):
+        chunk = pairs[off:off + group_size]
+        dw, _, _ = blocksparse_reduced_dw([p[0] for p in chunk], [p[1] for p in chunk], scale, dw, bsize=bsize, norm=norm, axis=axis)
+    return dw
+
+
+class _GatherRows(torch.autograd.Function):
+    """GatherScatter op (reference matmul.py:895-898): out[r] = x[idx[r]] (0 where idx < 0); the gradient is the same op
+    with the reverse table."""
+
+    @staticmethod
+    def forward(ctx, x, fwd_idx, bwd_idx, n_out):
+        ctx.fwd_idx, ctx.bwd_idx, ctx.n_in = fwd_idx, bwd_idx, x.shape[0]
+        return _gather_rows(x, None, fwd_idx, n_out, 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _gather_rows(dy.contiguous(), None, ctx.bwd_idx, ctx.n_in, 0), None, None, None
+
+
+class _ScatterAddMul(torch.autograd.Function):
+    """ScatterAddMul op (reference matmul.py:900-910): z = x (+|*) scatter(y)."""
+
+    @staticmethod
+    def forward(ctx, x, y, gather_idx, scatter_idx, op):
+        ctx.op, ctx.gather_idx, ctx.scatter_idx = op, gather_idx, scatter_idx
+        ctx.save_for_backward(x, y)
+        return _gather_rows(x, y, scatter_idx, x.shape[0], op)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y = ctx.saved_tensors
+        dz = dz.contiguous()
+        if ctx.op == 1:
+            return dz, _gather_rows(dz, None, ctx.gather_idx, y.shape[0], 0), None, None, None
+        dx = _gather_rows(dz, y, ctx.scatter_idx, x.shape[0], 2)                               # dz * scatter(y) (1 elsewhere)
+        dy = _gather_rows((dz * x).contiguous(), None, ctx.gather_idx, y.shape[0], 0)          # gather(dz * x)
+        return dx, dy, None, None, None
+
+
+def _gather_rows(x, y, idx, n_out, op):
+    if not x.is_cuda:
+        raise _lib.BsmmError("SparseProj needs CUDA tensors (no CPU path)")
+    x2 = x.reshape(x.shape[0], -1).contiguous()
+    y2 = None if y is None else y.reshape(y.shape[0], -1).contiguous()
+    out = torch.empty((n_out,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bsmm_gather_rows(_lib.dtype_code(x.dtype), x2.data_ptr(), _lib.ptr(y2), idx.data_ptr(), out.data_ptr(),
+                                          n_out, x2.shape[1], op, _lib.stream_ptr())
+    _lib.check(rc, "bsmm_gather_rows")
+    return out
+
+
+class SparseProj(object):
+    """Drop-in for blocksparse.matmul.SparseProj (reference matmul.py:835-921): a fixed sparse projection of the feature
+    axis (axis 0 of (features, N) activations) by row gather / scatter, differentiable."""
+
+    def __getstate__(self):
+        return (self.nhidden, self.nproj, self.gather_lut, self.name)
+
+    def __setstate__(self, state):
+        self.__init__(state[0], nproj=state[1], gather_lut=state[2], name=state[3])
+
+    def __init__(self, nhidden, nproj=None, proj_stride=None, block_size=32, gather_lut=None, name=None):
+        if gather_lut is None:
+            gather_lut = np.arange(nhidden, dtype=np.int32)
+            if nproj is not None:
+                assert nproj <= nhidden
+                np.random.shuffle(gather_lut)
+                gather_lut = np.sort(gather_lut[0:nproj])
+            elif proj_stride is not None:
+                assert proj_stride <= nhidden
+                gather_max = ((nhidden // proj_stride) // block_size) * block_size * proj_stride
+                gather_lut = gather_lut[:gather_max:proj_stride].copy()
+            else:
+                raise ValueError("missing nproj, proj_stride or gather_lut")
+        gather_lut = np.asarray(gather_lut, dtype=np.int32)
+        nproj = int(gather_lut.size)
+        scatter_lut = np.full(nhidden, -1, dtype=np.int32)
+        scatter_lut[gather_lut] = np.arange(nproj, dtype=np.int32)
+        self.name = name or "SparseProj"
+        self.gather_lut, self.scatter_lut = gather_lut, scatter_lut
+        self.nhidden, self.nproj = nhidden, nproj
+        self._dev = {}
+
+    def _luts(self, device):
+        key = (device.type, device.index)
+        if key not in self._dev:
+            self._dev[key] = (torch.as_tensor(self.gather_lut, device=device), torch.as_tensor(self.scatter_lut, device=device))
+        return self._dev[key]
+
+    def gather(self, x):
+        assert x.shape[0] == self.nhidden
+        g, s = self._luts(x.device)
+        return _GatherRows.apply(x.contiguous(), g, s, self.nproj)
+
+    def scatter(self, x):
+        assert x.shape[0] == self.nproj
+        g, s = self._luts(x.device)
+        return _GatherRows.apply(x.contiguous(), s, g, self.nhidden)
+
+    def scatter_add(self, x, y):
+        assert x.shape[0] == self.nhidden and y.shape[0] == self.nproj
+        g, s = self._luts(x.device)
+        return _ScatterAddMul.apply(x.contiguous(), y.contiguous(), g, s, 1)
+
+    def scatter_mul(self, x, y):
+        assert x.shape[0] == self.nhidden and y.shape[0] == self.nproj
+        g, s = self._luts(x.device)
+        return _ScatterAddMul.apply(x.contiguous(), y.contiguous(), g, s, 2)

@@ -12,10 +12,11 @@ import numpy as np
 import torch
 
 from . import _lib
+from .checkers import TransformerCheckers
 from .lut import TransformerLuts
 
 
-class BlocksparseTransformer(object):
+class BlocksparseTransformer(TransformerCheckers):
     """Drop-in for blocksparse.transformer.BlocksparseTransformer (reference transformer.py:51)."""
 
     def __getstate__(self):

@@ -18,6 +18,15 @@
  *   bst_softmax           <- BlocksparseMaskedSoftmax<T,V> (src/bst_op.cc:331-340,374-428)
  *   bst_softmax_grad      <- BlocksparseSoftmaxGrad<T,V>   (src/bst_op.cc:443-512)
  *   bst_autoregressive_mask <- BstPartialAutoregressiveMask (src/bst_op.cc:519-575)
+ *   bsmm_block_norm / bsmm_l2_decay / bsmm_threshold_prune / bsmm_prune_topk
+ *                         <- BlocksparseNorm / BlocksparseL2Decay / BlocksparseThresholdPrune / BlocksparsePrune
+ *                            (src/optimize_op_gpu.cu:794-1098)
+ *   bsmm_identity_init    <- IdentityInitCK (src/blocksparse_matmul_op_gpu.cu:2988-3028)
+ *   bsmm_l2_normalize(_grad) <- L2NormalizeCK / L2NormalizeGainCK and their gradients
+ *                            (src/blocksparse_l2_norm_op_gpu.cu:150-234,593-708)
+ *   bsmm_reduced_dw       <- BlocksparseReducedDWOp: BlocksparseFeatureReduce{CN,NC} + hGemm{NT,TN}
+ *                            (src/blocksparse_matmul_op.cc:639-773)
+ *   bsmm_gather_rows      <- GatherScatter / ScatterAddMul ops behind SparseProj (blocksparse/matmul.py:835-921)
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer except `err` strings is DEVICE memory
@@ -206,6 +215,39 @@ int bst_softmax_grad(int dtype, int dx_dtype, int bsize,
 int bst_autoregressive_mask(int bsize, const int32_t* nt_lut, int lut_heads, int blocks,
                             const void* mask_in, void* mask_out, int autoregress_at_key,
                             void* stream);
+
+/* ---- utilities on the (blocks, bsize, bsize) weight format -------------------------------------- */
+
+/* norm[b] = max|w| (norm_type 0) or sqrt(sum w^2) (norm_type 1) of block b; norm is float[blocks]. */
+int bsmm_block_norm(int dtype, int bsize, int blocks, const void* w, float* norm, int norm_type, void* stream);
+/* In place: w[b] -= w[b] * min(rate / sqrt(sum(w[b]^2) + epsilon), 1); blocks whose gate is 0 are skipped (gate may be NULL). */
+int bsmm_l2_decay(int dtype, int bsize, int blocks, void* w, const float* gate, float rate, float epsilon, void* stream);
+/* gate[b] = norm(w[b]) < threshold ? 0 : 1 */
+int bsmm_threshold_prune(int dtype, int bsize, int blocks, const void* w, float* gate, float threshold, int norm_type, void* stream);
+/* idx = block ids sorted by decreasing norm: gate[idx[i]] = i < keep ? 1 : 0 */
+int bsmm_prune_topk(float* gate, const int32_t* idx, int blocks, int keep, void* stream);
+/* W[b] = scale * I for blocks with (c % KB) == (k % CB), 0 elsewhere; updat_lut = int32 [blocks][2] = (c, k). */
+int bsmm_identity_init(int dtype, int bsize, int blocks, const int32_t* updat_lut, int n_c_blocks, int n_k_blocks, void* w, float scale, void* stream);
+/* y[w][i][j] = gain[k*bs + j] * w[w][i][j] / sqrt(max(sum_sqr[k*bs + j], epsilon)), the sum running over every row of every
+ * block of OUTPUT block column k (lut = the fprop row LUT, n_out = KB); sum_sqr (float[KB*bsize]) is kept for the gradient.
+ * gain may be NULL.  y_dtype: the weight dtype or fp32. */
+int bsmm_l2_normalize(int dtype, int y_dtype, int bsize, const int32_t* lut, int n_out, const void* w, const float* gain, void* y,
+                      float* sum_sqr, float epsilon, void* stream);
+/* dx (weight dtype), dg (float[KB*bsize], NULL without gain):
+ * dx = (dy*g + w * (sum_sqr >= eps) * sum(-dy*g*w / max(sum_sqr, eps))) / sqrt(max(sum_sqr, eps));  dg = sum(dy * w / norm) */
+int bsmm_l2_normalize_grad(int dtype, int y_dtype, int bsize, const int32_t* lut, int n_out, const void* dy, const void* w, const float* gain,
+                           const float* sum_sqr, void* dx, float* dg, float epsilon, void* stream);
+/* Block-reduced FULL weight gradient for network growth: x_red / y_red = per-block max|.| (norm_type 0) or l2 norm over the
+ * bsize features of each block of every x_p / dy_p (layout (pair, n, block) for axis 1, (block, pair, n) for axis 0, activation
+ * dtype), then dw[bC][bK] (float) = scale * sum_{p,n} x_red * y_red (+ dw when accumulate).  scale == 0 skips the reductions.
+ * workspace: bsmm_reduced_dw_workspace_bytes(bC, bK) bytes of device memory. */
+size_t bsmm_reduced_dw_workspace_bytes(int n_c_blocks, int n_k_blocks);
+int bsmm_reduced_dw(int dtype, int axis, int bsize, const void* const* xs, const void* const* dys, int pcount,
+                    int n_c_blocks, int n_k_blocks, int N, float scale, int norm_type, float* dw, int accumulate,
+                    void* x_red, void* y_red, void* workspace, void* stream);
+/* Row gather / scatter on (rows, N) activations (SparseProj): op 0: out[r] = idx[r] >= 0 ? x[idx[r]] : 0;
+ * op 1: out[r] = x[r] + (idx[r] >= 0 ? y[idx[r]] : 0);  op 2: out[r] = x[r] * (idx[r] >= 0 ? y[idx[r]] : 1). */
+int bsmm_gather_rows(int dtype, const void* x, const void* y, const int32_t* idx, void* out, int rows, long long N, int op, void* stream);
 
 /* ---- measurement helper (the reference's `bench` op attribute, op.cc:99-106) ---------
  * Records two events around whatever the caller enqueues between begin and end.      */

@@ -197,6 +197,35 @@ def gen_transformer(tr):
         print("wrote", name, "blocks", ref.blocks, "nn_max", ref.nn_max, "tn_max", ref.tn_max)
 
 
+def gen_wutil(mm):
+    """l2_normalize_test / l2_normalize_grad_test (matmul.py:421-443) on seeded inputs -> wutil_*.npz."""
+    import scipy.sparse as sparse
+    real_find = sparse.find
+
+    def find_colmajor(csr):
+        r, c, v = real_find(csr)
+        order = np.lexsort((r, c))
+        return r[order], c[order], v[order]
+
+    rng = np.random.default_rng(20260924)
+    lays = {"rand_6x7": (rng.random((6, 7)) < 0.45).astype(np.int32), "dense_3x3": np.ones((3, 3), np.int32)}
+    lays["rand_6x7"][0, 0] = 1
+    lays["rand_6x7"][:, 5] = 0                      # an empty output column
+    for name, lay in lays.items():
+        for bsize in (8, 16, 32):
+            mm.sparse.find = find_colmajor
+            try:
+                ref = mm.BlocksparseMatMul(lay.copy(), block_size=bsize, feature_axis=0)
+            finally:
+                mm.sparse.find = real_find
+            W = rng.normal(0, 1.0, ref.w_shape).astype(np.float32)
+            U = rng.normal(0, 1.0, ref.w_shape).astype(np.float32)
+            rec = dict(layout=lay, bsize=bsize, W=W, U=U,
+                       Y=ref.l2_normalize_test(W.copy()), DX=ref.l2_normalize_grad_test(W.copy(), U.copy()))
+            np.savez_compressed(os.path.join(HERE, "wutil_%s_bs%d.npz" % (name, bsize)), **rec)
+            print("wrote wutil", name, bsize)
+
+
 if __name__ == "__main__":
     mm, tr = import_reference()
     gen_matmul(mm)
