@@ -274,6 +274,18 @@ int bst_softmax(int x_dtype, int y_dtype, int bsize,
   p.autoregress_at_key = autoregress_at_key;
   p.x = x; p.y = y; p.scale = scale;
   p.batch = batch; p.heads = heads; p.blocks = blocks; p.ctx_blks_q = ctx_blks_q;
+  // TMA-staged kernel: 16-bit tensors, 32 x 32 / 64 x 64 blocks, every row's blocks fit shared memory (<= 16 of them)
+  static const bool no_staged = [] { const char* e = getenv("BSMM_SOFTMAX_STAGED"); return e && atoi(e) == 0; }();
+  if (!no_staged && x_dtype != BSMM_F32 && y_dtype != BSMM_F32 && (bsize == 32 || bsize == 64) && max_lut >= 1 && max_lut <= 16 &&
+      (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && device_info().ok && device_info().cc_major >= 9) {
+#define BSMM_SM_STAGED(TXT, TYT)                                                                              \
+    return bsize == 64 ? launch_softmax_staged<TXT, TYT, 64>(p, max_lut, s) : launch_softmax_staged<TXT, TYT, 32>(p, max_lut, s);
+    if (x_dtype == BSMM_BF16 && y_dtype == BSMM_BF16) { BSMM_SM_STAGED(__nv_bfloat16, __nv_bfloat16) }
+    if (x_dtype == BSMM_BF16 && y_dtype == BSMM_F16)  { BSMM_SM_STAGED(__nv_bfloat16, __half) }
+    if (x_dtype == BSMM_F16 && y_dtype == BSMM_F16)   { BSMM_SM_STAGED(__half, __half) }
+    if (x_dtype == BSMM_F16 && y_dtype == BSMM_BF16)  { BSMM_SM_STAGED(__half, __nv_bfloat16) }
+#undef BSMM_SM_STAGED
+  }
   BSMM_DISPATCH_DTYPE(x_dtype, TX, {
     BSMM_DISPATCH_DTYPE(y_dtype, TY, {
       BSMM_DISPATCH_BSIZE(bsize, BS, {
@@ -299,6 +311,17 @@ int bst_softmax_grad(int dtype, int dx_dtype, int bsize,
   p.nn_head_stride = lut_heads > 1 ? 2LL * (ctx_blks_q + blocks) : 0;
   p.x = dy; p.y_in = y; p.y = dx; p.scale = scale;
   p.batch = batch; p.heads = heads; p.blocks = blocks; p.ctx_blks_q = ctx_blks_q;
+  static const bool no_staged = [] { const char* e = getenv("BSMM_SOFTMAX_STAGED"); return e && atoi(e) == 0; }();
+  if (!no_staged && dtype != BSMM_F32 && dx_dtype != BSMM_F32 && (bsize == 32 || bsize == 64) && max_lut >= 1 && max_lut <= 16 &&
+      (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) == 0 && device_info().ok && device_info().cc_major >= 9) {
+#define BSMM_SG_STAGED(TT, TDT)                                                                               \
+    return bsize == 64 ? launch_softmax_grad_staged<TT, TDT, 64>(p, max_lut, s) : launch_softmax_grad_staged<TT, TDT, 32>(p, max_lut, s);
+    if (dtype == BSMM_BF16 && dx_dtype == BSMM_BF16) { BSMM_SG_STAGED(__nv_bfloat16, __nv_bfloat16) }
+    if (dtype == BSMM_F16 && dx_dtype == BSMM_F16)   { BSMM_SG_STAGED(__half, __half) }
+    if (dtype == BSMM_F16 && dx_dtype == BSMM_BF16)  { BSMM_SG_STAGED(__half, __nv_bfloat16) }
+    if (dtype == BSMM_BF16 && dx_dtype == BSMM_F16)  { BSMM_SG_STAGED(__nv_bfloat16, __half) }
+#undef BSMM_SG_STAGED
+  }
   BSMM_DISPATCH_DTYPE(dtype, T, {
     BSMM_DISPATCH_DTYPE(dx_dtype, TD, {
       BSMM_DISPATCH_BSIZE(bsize, BS, {

@@ -271,6 +271,13 @@ __device__ __forceinline__ void tmem_st_zero_x32(uint32_t taddr) {
       ::"r"(taddr), "r"(0u)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_zero_x16(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ---------------------------------------------------------------------------

@@ -222,6 +222,232 @@ bst_softmax_kernel(const SoftmaxParams p) {
   }
 }
 
+// ---- TMA-staged variant (16-bit in and out, 32 x 32 / 64 x 64 blocks, rows of <= MAXE key blocks) -------------------
+// One small CTA per (query block, 16-row chunk, head, batch).  Rows of a softmax are independent, and 16 consecutive rows of a
+// block are one contiguous 16*bs*2-byte piece of the sparse tensor: one thread pulls the chunk's piece of every block of the
+// row into shared memory with bulk async copies (one mbarrier), the 4 warps then own 4 query rows each -- a warp-wide
+// shared-memory access is one whole row of one block, conflict free -- keep the row's values in registers across max / exp /
+// sum / normalise, write the 16-bit results back IN PLACE, and one thread sends every piece to HBM with a bulk store.  HBM
+// sees each element exactly once in and once out, in 1-2 KB bursts, and with ~22 KB of shared memory per CTA ten CTAs share
+// an SM, so loads, arithmetic and stores of different chunks overlap.  (First version: one CTA per whole query block, 88 KB,
+// two per SM, phases serialised: 0.347 ms at cfg 3 against 0.165 ms for the register kernel, profiles/r2_softmax.txt.)
+constexpr int SOFTMAX_STAGED_THREADS = 128;
+constexpr int SOFTMAX_STAGED_ROWS = 16;
+
+template <typename TX, typename TY, int BS, int MAXE>
+__global__ void __launch_bounds__(SOFTMAX_STAGED_THREADS)
+bst_softmax_staged_kernel(const SoftmaxParams p) {
+  static_assert(sizeof(TX) == 2 && sizeof(TY) == 2 && (BS == 32 || BS == 64), "staged softmax: 16-bit, bs 32/64");
+  using MT = typename MaskWord<BS>::type;
+  constexpr int EPL = BS / 32;                    // elements per lane: a warp reads one row of one block per access
+  constexpr int RC = SOFTMAX_STAGED_ROWS, NCH = BS / RC;
+  constexpr uint32_t BLK_BYTES = RC * BS * 2;     // the chunk's piece of one block
+  extern __shared__ __align__(128) uint8_t sm_blocks[];
+  __shared__ uint64_t bar;
+  __shared__ int2 s_ent[MAXE];
+  const int q = blockIdx.x / NCH, row0 = (blockIdx.x % NCH) * RC, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int hl = p.nn_head_stride ? h : 0;
+  const int32_t* lut = p.nn_lut + (long long)hl * p.nn_head_stride;
+  const int first = lut[2 * q], count = lut[2 * q + 1];
+  if (count == 0) return;
+  const long long zoff = ((long long)b * p.heads + h) * p.blocks;
+  const int2* ent = reinterpret_cast<const int2*>(lut) + first;
+  if (tid < count) s_ent[tid] = ent[tid];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)count * BLK_BYTES) : "memory");
+    for (int e = 0; e < count; ++e) {
+      const TX* src = reinterpret_cast<const TX*>(p.x) + (zoff + s_ent[e].x) * (long long)(BS * BS) + row0 * BS;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(sm_blocks + (size_t)e * BLK_BYTES)), "l"(src), "r"(BLK_BYTES), "r"(bar_a) : "memory");
+    }
+  }
+  {   // every thread waits for the data (parity 0: single use of the barrier)
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_a) : "memory");
+  }
+  const MT* mask = reinterpret_cast<const MT*>(p.mask);
+  if (mask) mask += (p.mask_head_stride ? (long long)h * p.mask_head_stride : 0);
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float sc2 = p.scale * LOG2E;              // work in the exp2 domain: v = x * scale * log2(e)
+  for (int lr = warp; lr < RC; lr += SOFTMAX_STAGED_THREADS / 32) {
+    const int row = row0 + lr;
+    float v[MAXE][EPL];
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < count) {
+        const TX* src = reinterpret_cast<const TX*>(sm_blocks + (size_t)e * BLK_BYTES) + lr * BS + lane * EPL;
+        if constexpr (EPL == 2) { const float2 t = load2<TX>(src); v[e][0] = t.x * sc2; v[e][1] = t.y * sc2; }
+        else v[e][0] = to_f32<TX>(*src) * sc2;
+        if (mask) {
+          uint64_t w = (uint64_t)mask[(long long)s_ent[e].x * BS + row];
+          if (p.autoregress_at_key >= 0) w = autoregress_word<BS>(w, p.autoregress_at_key, s_ent[e].y, q * BS + row);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) if (!((w >> (lane * EPL + i)) & 1ull)) v[e][i] = -FLT_MAX;
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) m = fmaxf(m, v[e][i]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float ssum = 0.f;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < count) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { v[e][i] = exp2f(v[e][i] - m); ssum += v[e][i]; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float inv = 1.f / ssum;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < count) {
+        TY* dst = reinterpret_cast<TY*>(sm_blocks + (size_t)e * BLK_BYTES) + lr * BS + lane * EPL;
+        if constexpr (EPL == 2) store2<TY>(dst, v[e][0] * inv, v[e][1] * inv);
+        else *dst = from_f32<TY>(v[e][0] * inv);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
+  __syncthreads();
+  if (tid == 0) {
+    for (int e = 0; e < count; ++e) {
+      TY* dst = reinterpret_cast<TY*>(p.y) + (zoff + s_ent[e].x) * (long long)(BS * BS) + row0 * BS;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(sm_blocks + (size_t)e * BLK_BYTES)), "r"(BLK_BYTES) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+  }
+}
+
+// Gradient, same decomposition: dy and y pieces are staged (2 x ~22 KB per CTA), dx = (dy - sum_row(dy*y)) * y * scale is
+// written over the dy piece and bulk-stored.
+template <typename T, typename TD, int BS, int MAXE>
+__global__ void __launch_bounds__(SOFTMAX_STAGED_THREADS)
+bst_softmax_grad_staged_kernel(const SoftmaxParams p) {
+  static_assert(sizeof(T) == 2 && sizeof(TD) == 2 && (BS == 32 || BS == 64), "staged softmax grad: 16-bit, bs 32/64");
+  constexpr int EPL = BS / 32;
+  constexpr int RC = SOFTMAX_STAGED_ROWS, NCH = BS / RC;
+  constexpr uint32_t BLK_BYTES = RC * BS * 2;
+  extern __shared__ __align__(128) uint8_t sm_blocks[];      // [count] dy pieces, then [count] y pieces
+  __shared__ uint64_t bar;
+  __shared__ int s_blk[MAXE];
+  const int q = blockIdx.x / NCH, row0 = (blockIdx.x % NCH) * RC, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int hl = p.nn_head_stride ? h : 0;
+  const int32_t* lut = p.nn_lut + (long long)hl * p.nn_head_stride;
+  const int first = lut[2 * q], count = lut[2 * q + 1];
+  if (count == 0) return;
+  const long long zoff = ((long long)b * p.heads + h) * p.blocks;
+  if (tid < count) s_blk[tid] = lut[2 * (first + tid)];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  uint8_t* sm_y = sm_blocks + (size_t)count * BLK_BYTES;
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * (uint32_t)count * BLK_BYTES) : "memory");
+    for (int e = 0; e < count; ++e) {
+      const long long off = (zoff + s_blk[e]) * (long long)(BS * BS) + row0 * BS;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(sm_blocks + (size_t)e * BLK_BYTES)), "l"(reinterpret_cast<const T*>(p.x) + off), "r"(BLK_BYTES), "r"(bar_a) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(sm_y + (size_t)e * BLK_BYTES)), "l"(reinterpret_cast<const T*>(p.y_in) + off), "r"(BLK_BYTES), "r"(bar_a) : "memory");
+    }
+  }
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_a) : "memory");
+  }
+  for (int lr = warp; lr < RC; lr += SOFTMAX_STAGED_THREADS / 32) {
+    float d[MAXE][EPL], y[MAXE][EPL];
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < count) {
+        const T* pd = reinterpret_cast<const T*>(sm_blocks + (size_t)e * BLK_BYTES) + lr * BS + lane * EPL;
+        const T* py = reinterpret_cast<const T*>(sm_y + (size_t)e * BLK_BYTES) + lr * BS + lane * EPL;
+        if constexpr (EPL == 2) { const float2 a = load2<T>(pd), c = load2<T>(py); d[e][0] = a.x; d[e][1] = a.y; y[e][0] = c.x; y[e][1] = c.y; }
+        else { d[e][0] = to_f32<T>(*pd); y[e][0] = to_f32<T>(*py); }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) acc += d[e][i] * y[e][i];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < count) {
+        TD* dst = reinterpret_cast<TD*>(sm_blocks + (size_t)e * BLK_BYTES) + lr * BS + lane * EPL;
+        if constexpr (EPL == 2) store2<TD>(dst, (d[e][0] - acc) * y[e][0] * p.scale, (d[e][1] - acc) * y[e][1] * p.scale);
+        else *dst = from_f32<TD>((d[e][0] - acc) * y[e][0] * p.scale);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    for (int e = 0; e < count; ++e) {
+      TD* dst = reinterpret_cast<TD*>(p.y) + (zoff + s_blk[e]) * (long long)(BS * BS) + row0 * BS;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(sm_blocks + (size_t)e * BLK_BYTES)), "r"(BLK_BYTES) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+template <typename T, typename TD, int BS>
+int launch_softmax_grad_staged(const SoftmaxParams& p, int max_lut, cudaStream_t s) {
+  dim3 grid(p.ctx_blks_q * (BS / SOFTMAX_STAGED_ROWS), p.heads, p.batch);
+  const size_t smem = (size_t)2 * max_lut * SOFTMAX_STAGED_ROWS * BS * 2;
+#define BSMM_STAGED(MAXE)                                                                                     \
+  { auto kern = bst_softmax_grad_staged_kernel<T, TD, BS, MAXE>;                                              \
+    static thread_local uint64_t cfg = 0;                                                                     \
+    if (int e = ensure_dyn_smem(kern, (size_t)2 * MAXE * SOFTMAX_STAGED_ROWS * BS * 2, cfg)) return e;        \
+    kern<<<grid, SOFTMAX_STAGED_THREADS, smem, s>>>(p); }
+  if (max_lut <= 4) BSMM_STAGED(4)
+  else if (max_lut <= 8) BSMM_STAGED(8)
+  else if (max_lut <= 12) BSMM_STAGED(12)
+  else BSMM_STAGED(16)
+#undef BSMM_STAGED
+  return check_launch("bst_softmax_grad_staged");
+}
+
+template <typename TX, typename TY, int BS>
+int launch_softmax_staged(const SoftmaxParams& p, int max_lut, cudaStream_t s) {
+  dim3 grid(p.ctx_blks_q * (BS / SOFTMAX_STAGED_ROWS), p.heads, p.batch);
+  const size_t smem = (size_t)max_lut * SOFTMAX_STAGED_ROWS * BS * 2;
+#define BSMM_STAGED(MAXE)                                                                                     \
+  { auto kern = bst_softmax_staged_kernel<TX, TY, BS, MAXE>;                                                  \
+    static thread_local uint64_t cfg = 0;                                                                     \
+    if (int e = ensure_dyn_smem(kern, (size_t)MAXE * SOFTMAX_STAGED_ROWS * BS * 2, cfg)) return e;            \
+    kern<<<grid, SOFTMAX_STAGED_THREADS, smem, s>>>(p); }
+  if (max_lut <= 4) BSMM_STAGED(4)
+  else if (max_lut <= 8) BSMM_STAGED(8)
+  else if (max_lut <= 12) BSMM_STAGED(12)
+  else BSMM_STAGED(16)
+#undef BSMM_STAGED
+  return check_launch("bst_softmax_staged");
+}
+
 template <typename T, typename TD, int BS>
 __global__ void __launch_bounds__(SOFTMAX_WARPS * 32)
 bst_softmax_grad_kernel(const SoftmaxParams p) {

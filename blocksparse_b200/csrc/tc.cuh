@@ -120,6 +120,11 @@ template <> struct XpropCfg<32, 2> {
   static constexpr int XS = 4, WPS = 8, STG = 2, NP = 4, TCOLS = 256;
   static constexpr uint32_t SWZ = ptx::SWZ_64B, SBO = 512;
 };
+// 16 x 16 blocks: 16-block tiles (256 TMEM columns), 32-byte operand rows (SWIZZLE_32B), one K=16 slice per block
+template <> struct XpropCfg<16, 2> {
+  static constexpr int XS = 8, WPS = 8, STG = 4, NP = 4, TCOLS = 256;
+  static constexpr uint32_t SWZ = ptx::SWZ_32B, SBO = 256;     // 8 rows of 32 bytes
+};
 template <> struct XpropCfg<64, 1> {
   static constexpr int XS = 4, WPS = 4, STG = 2, NP = 2, TCOLS = 512;
   static constexpr uint32_t SWZ = ptx::SWZ_128B, SBO = 1024;   // 128-byte rows
@@ -418,6 +423,18 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     // accumulators start from zero: clear this warp's lanes once, then after every read-out
 #pragma unroll
     for (int c = 0; c < Cfg::TCOLS; c += 32) ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c);
+    // columns handled per tcgen05.ld: 32, or the whole 16-column block of 16 x 16 blocks
+    constexpr int CW = BS < 32 ? BS : 32, NH = BS / CW;
+    auto ld_cols = [&](uint32_t col, uint32_t (&v)[32]) {
+      if constexpr (CW == 32) ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + col, v);
+      else { uint32_t t[16]; ptx::tmem_ld_x16(tmem + ((uint32_t)(quad * 32) << 16) + col, t);
+#pragma unroll
+             for (int i = 0; i < 16; ++i) v[i] = t[i]; }
+    };
+    auto zero_cols = [&](uint32_t col) {
+      if constexpr (CW == 32) ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + col);
+      else ptx::tmem_st_zero_x16(tmem + ((uint32_t)(quad * 32) << 16) + col);
+    };
     ptx::tmem_st_wait();
     ptx::tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -441,19 +458,19 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         uint16_t* ycol = reinterpret_cast<uint16_t*>(p.y) + (long long)first_out * BS * p.y_pitch + gcol;
         for (int slot = 0; slot < n_out; ++slot) {
 #pragma unroll
-          for (int h = 0; h < BS / 32; ++h) {
+          for (int h = 0; h < NH; ++h) {
             uint32_t v[32];
             if ((mask >> slot) & 1u) {
-              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
+              ld_cols((uint32_t)(slot * BS + h * 32), v);
               ptx::tmem_ld_wait();
-              ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32));
+              zero_cols((uint32_t)(slot * BS + h * 32));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;
             }
             if (gcol < p.N) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
+              for (int j = 0; j < CW; ++j) {
                 uint16_t o;
                 if (BF16) { __nv_bfloat16 q = __float2bfloat16_rn(__uint_as_float(v[j])); o = *reinterpret_cast<uint16_t*>(&q); }
                 else      { __half q = __float2half_rn(__uint_as_float(v[j]));            o = *reinterpret_cast<uint16_t*>(&q); }
@@ -472,19 +489,19 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + grow * p.y_pitch + (long long)first_out * BS;
         for (int slot = 0; slot < n_out; ++slot) {
 #pragma unroll
-          for (int h = 0; h < BS / 32; ++h) {
+          for (int h = 0; h < NH; ++h) {
             uint32_t v[32];
             if ((mask >> slot) & 1u) {
-              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
+              ld_cols((uint32_t)(slot * BS + h * 32), v);
               ptx::tmem_ld_wait();
-              ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32));
+              zero_cols((uint32_t)(slot * BS + h * 32));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;
             }
             if (grow < p.N) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
+              for (int c = 0; c < CW / 8; ++c) {
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -510,18 +527,18 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         for (int slot = s0; slot < s1; ++slot) {
           uint8_t* dst = sO + (slot - s0) * XBYTES + row * ROW;
 #pragma unroll
-          for (int h = 0; h < BS / 32; ++h) {            // 32 fp32 columns at a time
+          for (int h = 0; h < NH; ++h) {                 // 32 (16) fp32 columns at a time
             uint32_t v[32];
             if ((mask >> slot) & 1u) {
-              ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32), v);
+              ld_cols((uint32_t)(slot * BS + h * 32), v);
               ptx::tmem_ld_wait();
-              ptx::tmem_st_zero_x32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * BS + h * 32));
+              zero_cols((uint32_t)(slot * BS + h * 32));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = 0u;    // output block with an empty LUT row
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {                // four 16-byte chunks (8 elements each)
+            for (int c = 0; c < CW / 8; ++c) {           // 16-byte chunks (8 elements each)
               uint32_t pk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -530,7 +547,8 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
                 else      { __half2 q = __floats2half2_rn(a, b);           pk[e] = *reinterpret_cast<uint32_t*>(&q); }
               }
               const uint32_t chunk = h * 4 + c;                                  // 16-byte chunk index in the row
-              const uint32_t swz = (BS == 32) ? (chunk ^ ((row >> 1) & 3)) : (chunk ^ (row & 7));
+              // TMA swizzle of the staging tile: chunk ^= row bits (32B: (row/4)%2, 64B: (row/2)%4, 128B: row%8)
+              const uint32_t swz = (BS == 16) ? (chunk ^ ((row >> 2) & 1)) : (BS == 32) ? (chunk ^ ((row >> 1) & 3)) : (chunk ^ (row & 7));
               *reinterpret_cast<uint4*>(dst + swz * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
@@ -571,7 +589,7 @@ int launch_tc_xprop(const XpropTcParams& p, const XpropTmaps& maps, int sm_count
   const int total = p.n_ktiles * p.n_ntiles;
   const int grid = total < sm_count * OCC ? total : sm_count * OCC;
   kern<<<grid, xprop_threads<XpropCfg<BS, OCC, VAR>>(), smem, s>>>(p, maps);
-  return check_launch(BS == 32 ? "tcgen05_xprop_bs32" : "tcgen05_xprop_bs64");
+  return check_launch(BS == 16 ? "tcgen05_xprop_bs16" : BS == 32 ? "tcgen05_xprop_bs32" : "tcgen05_xprop_bs64");
 }
 
 inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lut, int n_out, int n_in, int blocks,
@@ -579,7 +597,7 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
                     int sched_groups_off, int order_off, int order_ntiles, cudaStream_t s) {
   (void)lut;
   if (dtype != BSMM_F16 && dtype != BSMM_BF16) { fail(0, "fp32 runs on the FMA path"); return TC_NOT_APPLICABLE; }
-  if (bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
+  if (bsize != 16 && bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
   if (gate != nullptr) { fail(0, "gated xprop uses the CUDA-core path"); return TC_NOT_APPLICABLE; }
   if (axis == 0 && (N & 7)) { fail(0, "feature_axis 0 needs N %% 8 == 0 for TMA (row pitch multiple of 16 bytes)"); return TC_NOT_APPLICABLE; }
   if (sched == nullptr || sched_tiles <= 0) { fail(0, "no tile schedule supplied"); return TC_NOT_APPLICABLE; }
@@ -595,7 +613,7 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   const uint64_t Cin = (uint64_t)n_in * bsize, Cout = (uint64_t)n_out * bsize;
   XpropTmaps maps;
-  const CUtensorMapSwizzle swz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle swz = bsize == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   if (axis == 1) {
     if (int e = cached_tmap_2d(&maps.x, dtype, x, Cin, (uint64_t)N, Cin, bsize, 128, swz)) return e;
   } else {       // (C, N): inner dim = minibatch; box = 64 columns x bs feature rows, 128-byte rows
@@ -623,6 +641,11 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
       sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
     return fail(BSMM_E_ARG, "bsmm_xprop: inconsistent tile schedule (n_tiles=%d, blocks_per_tile=%d, n_out=%d)",
                 p.n_ktiles, tile_blocks, n_out);
+  if (bsize == 16) {
+    if (occ != 2 || (w_per_group != 0 && w_per_group != 8))
+      return fail(BSMM_E_ARG, "bsmm_xprop: 16 x 16 blocks need 16-block tiles and 8 W blocks per group");
+    return dtype == BSMM_BF16 ? launch_tc_xprop<16, true, 2>(p, maps, dev.sm_grid, s) : launch_tc_xprop<16, false, 2>(p, maps, dev.sm_grid, s);
+  }
   if (occ == 2 && bsize == 32 && w_per_group == 4) {
     return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 3>(p, maps, dev.sm_grid, s)
                               : launch_tc_xprop<32, false, 2, 3>(p, maps, dev.sm_grid, s);

@@ -26,6 +26,9 @@ namespace bsmm {
 constexpr int UPDAT_THREADS = 7 * 32;
 constexpr int UPDAT_STAGES = 4;
 constexpr int UPDAT_KCHUNK = 64;        // minibatch rows per stage
+// record layout of lut.py:build_updat_schedule: 64 ints for <= 8 slots per tile (bs 32 / 64), 192 for the 16 slots of bs 16
+__host__ __device__ constexpr int updat_rec_ints(int bs) { return bs >= 32 ? 64 : 192; }
+__host__ __device__ constexpr int updat_tab_off(int bs) { return bs >= 32 ? 16 : 32; }
 
 struct UpdatTcParams {
   const int32_t* sched;     // build_updat_schedule
@@ -51,8 +54,9 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
   constexpr uint32_t ABYTES = 128 * UPDAT_KCHUNK * 2; // 16 KB: two 64-feature x 64-row boxes (SW128)
   constexpr uint32_t BSLOT = BS * UPDAT_KCHUNK * 2;   // 4 KB (bs 32, SW64) / 8 KB (bs 64, SW128)
   constexpr uint32_t STAGE_BYTES = ABYTES + KT * BSLOT;
-  constexpr uint32_t B_SWZ = (BS == 32) ? ptx::SWZ_64B : ptx::SWZ_128B;
-  constexpr uint32_t B_SBO = (BS == 32) ? 512 : 1024;       // 8 rows of BS*2 bytes
+  constexpr uint32_t B_SWZ = (BS == 16) ? ptx::SWZ_32B : (BS == 32) ? ptx::SWZ_64B : ptx::SWZ_128B;
+  constexpr uint32_t B_SBO = 8 * BS * 2;                    // 8 rows of BS*2 bytes
+  constexpr int REC = updat_rec_ints(BS), TAB = updat_tab_off(BS);   // record stride / offset of the W-id table (lut.py)
   constexpr uint32_t B_KSTEP = 16 * BS * 2;                 // 16 minibatch rows
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -91,7 +95,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
       const int t = tile_queue_next(&tq, tk, lane, abort_flag);
       if (t < 0) break;
       if (fetcher) drawn = tile_queue_draw(p.counter, tk + 1);
-      const int32_t* rec = recs + (size_t)t * 64;
+      const int32_t* rec = recs + (size_t)t * REC;
       const int c0 = rec[0], n_act = rec[1];
       const int my_k = (lane >= 2 && lane < 2 + n_act) ? rec[8 + lane - 2] : 0;
       int ch = (int)((2 + warp - (sbase % 2)) % 2);
@@ -135,7 +139,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
     for (; alive; ++tile_it) {
       const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
       if (t < 0) break;
-      const int n_act = recs[(size_t)t * 64 + 1];
+      const int n_act = recs[(size_t)t * REC + 1];
       const uint32_t buf = tile_it & 1;
       const uint32_t idesc = ptx::make_idesc_f16(BF16, !p.axis0, !p.axis0, 128, n_act * BS);
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty[buf], ((tile_it >> 1) & 1) ^ 1, abort_flag))) { g_tc_error = 13; break; }
@@ -162,14 +166,15 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;                          // TMEM lanes [32*quad, 32*quad+32)
-    const int blk_i = (quad * 32) / BS;                 // input block of the group these lanes belong to
-    const int row = (quad * 32) % BS + lane;            // row inside the BS x BS block
+    const int blk_i = (quad * 32 + lane) / BS;          // input block of the group this lane's feature row belongs to
+    const int row = (quad * 32 + lane) % BS;            // row inside the BS x BS block
+    constexpr int CW = BS < 32 ? BS : 32, NH = BS / CW; // columns per tcgen05.ld
     TO* dw = reinterpret_cast<TO*>(p.dw);
     uint32_t tile_it = 0;
     for (;; ++tile_it) {
       const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
       if (t < 0) break;
-      const int32_t* rec = recs + (size_t)t * 64;
+      const int32_t* rec = recs + (size_t)t * REC;
       const int n_act = rec[1];
       const uint32_t buf = tile_it & 1;
       ptx::mbar_wait(&acc_full[buf], (tile_it >> 1) & 1, abort_flag);
@@ -177,23 +182,27 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
       if (*abort_flag) { g_tc_error = 16; break; }
       ptx::tc_fence_after();
       for (int s = 0; s < n_act; ++s) {
-        const int w = rec[16 + blk_i * p.k_per_tile + s];        // warp-uniform
-        if (w < 0) continue;
+        const int w = rec[TAB + blk_i * p.k_per_tile + s];       // warp-uniform for bs >= 32; two blocks per warp for bs 16
+        if (!__any_sync(0xffffffffu, w >= 0)) continue;          // tcgen05.ld is warp-collective: skip only when no lane stores
         float g = p.alpha;
-        if (p.gated) g *= p.gate[w];
-        TO* out = dw + ((size_t)w * BS + row) * BS;
+        if (p.gated && w >= 0) g *= p.gate[w];
+        TO* out = dw + ((size_t)(w >= 0 ? w : 0) * BS + row) * BS;
 #pragma unroll
-        for (int h = 0; h < BS / 32; ++h) {
+        for (int h = 0; h < NH; ++h) {
           uint32_t v[32];
-          ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + buf * 256 + (uint32_t)(s * BS + h * 32), v);
+          if constexpr (CW == 32) ptx::tmem_ld_x32(tmem + ((uint32_t)(quad * 32) << 16) + buf * 256 + (uint32_t)(s * BS + h * 32), v);
+          else { uint32_t t16[16]; ptx::tmem_ld_x16(tmem + ((uint32_t)(quad * 32) << 16) + buf * 256 + (uint32_t)(s * BS), t16);
+#pragma unroll
+                 for (int i = 0; i < 16; ++i) v[i] = t16[i]; }
           ptx::tmem_ld_wait();
+          if (w < 0) continue;
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * g;
+          for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]) * g;
           if (sizeof(TO) == 4) {
             float4* o4 = reinterpret_cast<float4*>(out + h * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < CW / 4; ++i) {
               float4 q = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
               if (p.beta != 0.f) { const float4 o = o4[i]; q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w; }
               o4[i] = q;
@@ -201,7 +210,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
           } else {
             uint4* o4 = reinterpret_cast<uint4*>(out + h * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < CW / 8; ++i) {
               uint32_t pk[4];
               uint4 old = make_uint4(0, 0, 0, 0);
               if (p.beta != 0.f) old = o4[i];
@@ -252,7 +261,7 @@ int launch_tc_updat(const UpdatTcParams& p, const UpdatTmaps& maps, int sm_count
   if (int e = ensure_dyn_smem(kern, smem, configured)) return e;
   const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
   kern<<<grid, UPDAT_THREADS, smem, s>>>(p, maps);
-  return check_launch(BS == 32 ? "tcgen05_updat_bs32" : "tcgen05_updat_bs64");
+  return check_launch(BS == 16 ? "tcgen05_updat_bs16" : BS == 32 ? "tcgen05_updat_bs32" : "tcgen05_updat_bs64");
 }
 
 inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t* updat_lut, int blocks, int n_c_blocks,
@@ -262,7 +271,7 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   (void)updat_lut; (void)blocks; (void)sched_groups_off;
   if (dtype != BSMM_F16 && dtype != BSMM_BF16) { fail(0, "fp32 runs on the FMA path"); return TC_NOT_APPLICABLE; }
   if (axis == 0 && (N & 7)) { fail(0, "feature_axis 0 needs N %% 8 == 0 for TMA"); return TC_NOT_APPLICABLE; }
-  if (bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
+  if (bsize != 16 && bsize != 32 && bsize != 64) { fail(0, "block size %d uses the CUDA-core path", bsize); return TC_NOT_APPLICABLE; }
   if (sched == nullptr || sched_tiles <= 0) { fail(0, "no updat schedule supplied"); return TC_NOT_APPLICABLE; }
   if (sched_tile_blocks != 256 / bsize) return fail(BSMM_E_ARG, "bsmm_updat: schedule built for %d slots per tile, kernel needs %d", sched_tile_blocks, 256 / bsize);
   if (N <= 0) return TC_NOT_APPLICABLE;
@@ -277,7 +286,7 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   const uint64_t C = (uint64_t)n_c_blocks * bsize, K = (uint64_t)n_k_blocks * bsize;
   UpdatTmaps maps;
   memset(&maps, 0, sizeof(maps));
-  const CUtensorMapSwizzle bswz = bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle bswz = bsize == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : bsize == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int i = 0; i < pcount; ++i) {
     if (axis == 1) {
       if (int e = cached_tmap_2d(&maps.x[i], dtype, xs[i], C, (uint64_t)N, C, 64, UPDAT_KCHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
@@ -295,6 +304,10 @@ inline int tc_updat(int dtype, int dw_dtype, int axis, int bsize, const int32_t*
   if (!p.counter && !static_tiles()) return fail(BSMM_E_NODEV, "bsmm_updat: tile counters not available");
   const bool bf = dtype == BSMM_BF16;
   const bool f32out = dw_dtype == BSMM_F32;
+  if (bsize == 16) {
+    if (f32out) return bf ? launch_tc_updat<16, true, float>(p, maps, dev.sm_grid, s) : launch_tc_updat<16, false, float>(p, maps, dev.sm_grid, s);
+    return bf ? launch_tc_updat<16, true, __nv_bfloat16>(p, maps, dev.sm_grid, s) : launch_tc_updat<16, false, __half>(p, maps, dev.sm_grid, s);
+  }
   if (bsize == 32) {
     if (f32out) return bf ? launch_tc_updat<32, true, float>(p, maps, dev.sm_grid, s) : launch_tc_updat<32, false, float>(p, maps, dev.sm_grid, s);
     return bf ? launch_tc_updat<32, true, __nv_bfloat16>(p, maps, dev.sm_grid, s) : launch_tc_updat<32, false, __half>(p, maps, dev.sm_grid, s);

@@ -456,7 +456,12 @@ def build_pair_schedule(outs, ins, wids, n_out, blocks_per_tile, w_per_group, n_
     return sched, grp_off, list_off
 
 
-UPDAT_REC_INTS = 64      # one 256-byte record per updat tile
+UPDAT_REC_INTS = 64      # one 256-byte record per updat tile (<= 8 slots: bs 32 / 64); bs 16 uses 192 ints (16 slots x 8 input blocks)
+
+
+def updat_record_shape(bsize):
+    """(ints per tile record, offset of the W-id table) -- mirrors csrc/tc_updat.cuh:updat_rec_ints / updat_tab_off."""
+    return (64, 16) if bsize >= 32 else (192, 32)
 
 
 def _updat_makespan(g_cnt, g_nwin, n_cta):
@@ -512,7 +517,8 @@ def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None, n_cta=None):
     if k_per_tile is None:
         k_per_tile = 256 // bsize
     KT = int(k_per_tile)
-    assert KT * bsize <= 256 and 16 + G * KT <= UPDAT_REC_INTS
+    REC, TAB = updat_record_shape(bsize)
+    assert KT * bsize <= 256 and 8 + KT <= TAB and TAB + G * KT <= REC
     lut = np.asarray(updat_lut, dtype=np.int64).reshape(-1, 2)
     cs, ks = lut[:, 0], lut[:, 1]
     wid = np.arange(len(cs), dtype=np.int64)
@@ -550,9 +556,9 @@ def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None, n_cta=None):
     rank[order] = np.arange(n_tiles)
 
     off = 4
-    sched = np.full(off + UPDAT_REC_INTS * n_tiles, -1, dtype=np.int32)
-    sched[0:4] = (n_tiles, G, KT, UPDAT_REC_INTS)
-    rec = sched[off:].reshape(n_tiles, UPDAT_REC_INTS)
+    sched = np.full(off + REC * n_tiles, -1, dtype=np.int32)
+    sched[0:4] = (n_tiles, G, KT, REC)
+    rec = sched[off:].reshape(n_tiles, REC)
     rec[:, 0:8] = 0
     t_of_u = rank[tile_idx_of_u]
     rec[t_of_u, 0] = (u_tile // n_win) * G
@@ -560,7 +566,7 @@ def build_updat_schedule(updat_lut, CB, KB, bsize, k_per_tile=None, n_cta=None):
     rec[t_of_u, 8 + slot_of_u] = u_k
     # blocks
     t_of_blk = rank[tile_idx_of_u[inv]]
-    rec[t_of_blk, 16 + (cs % G) * KT + slot_of_u[inv]] = wid
+    rec[t_of_blk, TAB + (cs % G) * KT + slot_of_u[inv]] = wid
     return sched, off
 
 

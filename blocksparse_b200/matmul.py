@@ -19,7 +19,7 @@ from .lut import MatmulLuts, pick_tile_count
 # (profiles/r1_xprop_tuning.txt): 32x32 blocks run best as half-width tiles (8 blocks = 256 TMEM columns) with two
 # CTAs per SM, 64x64 blocks as full-width tiles (8 blocks = 512 columns) with one.  BSMM_XPROP_OCC=1|2 forces one.
 _OCC_ENV = os.environ.get("BSMM_XPROP_OCC", "")
-_OCC = {32: 2, 64: 1} if _OCC_ENV not in ("1", "2") else {32: int(_OCC_ENV), 64: int(_OCC_ENV)}
+_OCC = {16: 2, 32: 2, 64: 1} if _OCC_ENV not in ("1", "2") else {16: 2, 32: int(_OCC_ENV), 64: int(_OCC_ENV)}
 _WPG_OVERRIDE = int(os.environ.get("BSMM_XPROP_WPG", "0"))     # tuning aid: force the W-slots-per-stage variant (2 or 4)
 _TILE_BLOCKS = {bs: (256 if occ == 2 else 512) // bs for bs, occ in _OCC.items()}
 # W blocks per schedule group == W slots per pipeline stage of the kernel (XpropCfg::WPS)
@@ -30,7 +30,7 @@ _SCHED_CACHE_MAX = 16
 # explain why), so 0 -- the default -- keeps csrc/tc.cuh.
 _X2_VARIANTS = {1: (8, 2, 4), 2: (8, 2, 8), 3: (16, 1, 12)}
 _X2_FORCE = int(os.environ.get("BSMM_XPROP2", "0"))
-_W_PER_GROUP = {32: 8, 64: 2 if _OCC[64] == 2 else 4}
+_W_PER_GROUP = {16: 8, 32: 8, 64: 2 if _OCC[64] == 2 else 4}
 
 
 def _as_2d(t, axis, feat):

@@ -30,6 +30,9 @@ CASES = [
     (40, 33, 0.08, 1, 32),        # single row
     (20, 20, 1.0, 257, 32),       # dense layout: 16 pairs per group
     (64, 64, 0.2, 640, 32),       # many tiles per CTA
+    (9, 40, 0.3, 200, 16),        # 16 x 16 blocks: 16-block tiles, 32-byte swizzle
+    (33, 17, 0.15, 64, 16),
+    (12, 12, 1.0, 130, 16),
     (6, 9, 0.5, 130, 64),
     (16, 17, 0.3, 64, 64),
     (12, 12, 1.0, 300, 64),
@@ -115,6 +118,9 @@ UPDAT_CASES = [
     (40, 33, 0.08, 1, 32, 1),
     (20, 20, 1.0, 257, 32, 3),
     (64, 64, 0.2, 640, 32, 8),     # 8 (x, dy) pairs in one launch
+    (9, 40, 0.3, 200, 16, 2),      # 16 x 16 blocks: 8 input blocks per group, 16 slots per tile, two blocks per epilogue warp
+    (33, 17, 0.15, 64, 16, 1),
+    (12, 12, 1.0, 130, 16, 8),
     (6, 9, 0.5, 130, 64, 1),
     (16, 17, 0.3, 64, 64, 2),
     (12, 12, 1.0, 300, 64, 1),
@@ -266,3 +272,39 @@ def test_tc_xprop2_variants_match_oracle(case, dtype, axis, variant, monkeypatch
             "%s variant %d: l2 %.3e max %.3e" % (name, variant, l2, mx)
         again = fn(inp.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_TC)
         assert torch.equal(got, again)            # deterministic accumulation order
+
+
+def test_cuda_graph_capture_and_replay():
+    """The launches take their tensor maps by value and read schedules from device memory, so a step can be captured in a
+    CUDA graph: replaying it (no Python, no host-side descriptor work) reproduces the eager results bit for bit."""
+    rng = np.random.default_rng(21)
+    lay = layout(rng, 32, 32, 0.25)
+    bsmm = BlocksparseMatMul(lay, block_size=32, feature_axis=1)
+    N = 512
+    W = (torch.randn(bsmm.w_shape, device="cuda") * 0.1).bfloat16()
+    X = torch.randn(bsmm.i_shape(N), device="cuda").bfloat16()
+    E = torch.randn(bsmm.o_shape(N), device="cuda").bfloat16()
+    ref = (bsmm.fprop(X, W), bsmm.bprop(E, W), bsmm.updat([X], [E]))      # also warms the schedule / tensor-map caches
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            bsmm.fprop(X, W); bsmm.bprop(E, W); bsmm.updat([X], [E])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y = bsmm.fprop(X, W)
+        dx = bsmm.bprop(E, W)
+        dw = bsmm.updat([X], [E])
+    for _ in range(3):
+        y.zero_(); dx.zero_(); dw.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref[0]) and torch.equal(dx, ref[1]) and torch.equal(dw, ref[2])
+    # new data in the captured input buffers
+    X.copy_(torch.randn_like(X.float()).bfloat16())
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y, bsmm.fprop(X, W))
+    assert _lib.device_error() == 0
