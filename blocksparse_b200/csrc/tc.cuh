@@ -224,7 +224,12 @@ struct XpropTcParams {
 };
 struct XpropTmaps { CUtensorMap x, w, y; };
 
-template <int BS, bool BF16, int OCC, int VAR = 0>
+// CL = 2: thread-block clusters of two CTAs that work on NEIGHBOURING OUTPUT TILES (2P, 2P+1) of the same minibatch tile and
+// walk one merged group list (lut.py:build_tile_schedule(pair_tiles=True)): the activation tile of group g is fetched by CTA
+// g % 2 and MULTICAST to both, so the activation panel crosses the L2 -> SM fabric once per tile PAIR instead of once per
+// tile -- the fabric (~12 TB/s for the chip) is what bounds this kernel (profiles/r2_xprop2_study.txt).  A stage may be
+// refilled once BOTH CTAs have retired its MMAs: every issuer's tcgen05.commit arrives on the empty barrier of both CTAs.
+template <int BS, bool BF16, int OCC, int VAR = 0, int CL = 1>
 __global__ void __launch_bounds__((xprop_threads<XpropCfg<BS, OCC, VAR>>()), OCC)
 tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) {
   using Cfg = XpropCfg<BS, OCC, VAR>;
@@ -250,13 +255,16 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   volatile int* abort_flag = &abort_s;
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const int total_tiles = p.n_ktiles * p.n_ntiles;
+  // CL == 2: the queue hands out tile PAIRS (index = minibatch tile * n_ktiles/2 + pair); this CTA takes output tile 2*pair + rank
+  const uint32_t crank = CL == 2 ? ptx::cluster_ctarank() : 0u;
+  const int kt_per = CL == 2 ? p.n_ktiles / 2 : p.n_ktiles;
+  const int total_tiles = kt_per * p.n_ntiles;
   const int32_t* sched = p.sched;
 
   if (tid == 0) {
     abort_s = 0;
     tile_queue_init(&tq, (int)(blockDim.x / 32));
-    for (int i = 0; i < XS; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < XS; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], CL); }
     ptx::mbar_init(&acc_full, NP);
     ptx::mbar_init(&acc_empty, 1);
     for (int i = 0; i < NP; ++i) ptx::mbar_init(&turn[i], 1);
@@ -266,6 +274,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   if (warp == NP) { ptx::tmem_alloc(&tmem_base_s, Cfg::TCOLS); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync();          // the peer's barriers are initialised before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -281,12 +290,13 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     const uint32_t p_bdesc_lo = (uint32_t)ptx::make_smem_desc(ptx::smem_u32(sStage) + XBYTES, p.bprop ? 16u : WBYTES, Cfg::SBO, Cfg::SWZ);
     const bool fetcher = warp == 0 && lane == 0;
     int drawn = 0;
-    if (fetcher) tile_queue_publish(&tq, 0, (int)blockIdx.x, p.order, total_tiles, abort_flag);
+    if (fetcher) tile_queue_publish(&tq, 0, (int)(blockIdx.x / CL), p.order, total_tiles, abort_flag);
     for (uint32_t tk = 0; alive; ++tk) {
       const int t = tile_queue_next(&tq, tk, lane, abort_flag);
       if (t < 0) break;
-      if (fetcher) drawn = tile_queue_draw(p.counter, tk + 1);            // for tile tk + 1; consumed after this tile's loads are issued
-      const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
+      if (fetcher) drawn = CL == 2 ? (int)(blockIdx.x / 2 + (tk + 1) * (gridDim.x / 2))     // clusters use the static deal
+                                   : tile_queue_draw(p.counter, tk + 1);   // for tile tk + 1; consumed after this tile's loads are issued
+      const int nt = t / kt_per, kt = CL * (t % kt_per) + (int)crank;
       const int32_t* th = sched + 4 + 4 * kt;
       const int first_group = th[0], n_groups = th[1];
       const int32_t* grec = sched + p.groups_off + (size_t)first_group * 32;
@@ -308,7 +318,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         // lanes 12..19 hold int0 of run (lane-12); int1 sits 8 lanes up.  They write the ready-to-issue
         // command so the issuing thread only moves registers.
         const uint32_t r1 = (uint32_t)__shfl_down_sync(0xffffffffu, cur, 8);
-        if (lane >= 12 && lane < 12 + n_runs) {
+        if (lane >= 12 && (lane < 12 + n_runs || lane == 12)) {      // lane 12 always writes: it carries the run count (0 for an empty group)
           const uint32_t r0 = (uint32_t)cur;
           ptx::st_shared_v4(cmd0 + st * (8 * 16) + (lane - 12) * 16,
                             (int)(p_bdesc_lo + ((st * STAGE_BYTES) >> 4) + (r0 & 0xffffu)),
@@ -319,7 +329,17 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
         const uint32_t stage = stage0 + st * STAGE_BYTES, fbar = full0 + st * 8;
         if (lane == 0) {
           ptx::mbar_expect_tx_a(fbar, XBYTES + (uint32_t)n_w * WBYTES);
-          if (!p.axis0) {
+          if (CL == 2) {
+            // both CTAs expect the activation tile; the CTA whose rank equals the group's parity fetches it for both
+            if ((g & 1) == (int)crank) {
+              if (!p.axis0) {
+                ptx::tma_load_2d_mc(stage, &maps.x, fbar, in_blk * BS, nt * 128, (uint16_t)3);
+              } else {
+                ptx::tma_load_2d_mc(stage, &maps.x, fbar, nt * 128, in_blk * BS, (uint16_t)3);
+                ptx::tma_load_2d_mc(stage + XBYTES / 2, &maps.x, fbar, nt * 128 + 64, in_blk * BS, (uint16_t)3);
+              }
+            }
+          } else if (!p.axis0) {
             ptx::tma_load_2d_a(stage, &maps.x, fbar, in_blk * BS, nt * 128);          // [128 n][bs c], K-major A
           } else {                                                                   // [bs c][128 n] as two 64-wide boxes, MN-major A
             ptx::tma_load_2d_a(stage, &maps.x, fbar, nt * 128, in_blk * BS);
@@ -358,7 +378,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     for (; alive; ++tile_it) {
       const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
       if (t < 0) break;
-      const int kt = t % p.n_ktiles;
+      const int kt = CL * (t % kt_per) + (int)crank;
       const int n_groups = sched[4 + 4 * kt + 1];
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(&acc_empty, tile_it & 1, abort_flag))) { g_tc_error = 3; break; }
       ptx::tc_fence_after();
@@ -402,7 +422,8 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
               else        ptx::mma_ss_a_use((uint32_t)c[r].y, adesc, bdesc, (uint32_t)c[r].z, 1u);
             }
           }
-          ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
+          if (CL == 2) ptx::tc_commit_mc(empty0 + st * 8, (uint16_t)3);   // ... in BOTH CTAs: the peer may multicast into this stage
+          else ptx::tc_commit_a(empty0 + st * 8);   // the stage is free once these MMAs retire
           ptx::tc_fence_before();
           ptx::mbar_arrive(&turn[iw + 1 == NP ? 0 : iw + 1]);     // hand the turn to the next issuer
         }
@@ -442,7 +463,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
     for (;; ++tile_it) {
       const int t = tile_queue_next(&tq, tile_it, lane, abort_flag);
       if (t < 0) break;
-      const int nt = t / p.n_ktiles, kt = t % p.n_ktiles;
+      const int nt = t / kt_per, kt = CL * (t % kt_per) + (int)crank;
       const int32_t* th = sched + 4 + 4 * kt;
       const int first_out = th[2];
       const int n_out = th[3] & 0xff;
@@ -570,6 +591,7 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync();          // nobody leaves while the peer may still signal this CTA's barriers
   if (warp == NP) ptx::tmem_dealloc(tmem, Cfg::TCOLS);
   if (tid == 0 && p.counter) tile_queue_retire(p.counter);
 }
@@ -578,6 +600,27 @@ template <int BS, int OCC, int VAR = 0>
 constexpr size_t xprop_smem_bytes() {
   using Cfg = XpropCfg<BS, OCC, VAR>;
   return (size_t)Cfg::XS * (128 * BS * 2 + Cfg::WPS * BS * BS * 2) + (size_t)Cfg::STG * 128 * BS * 2;
+}
+
+template <int BS, bool BF16, int OCC, int VAR>
+int launch_tc_xprop_pair(XpropTcParams p, const XpropTmaps& maps, int sm_count, cudaStream_t s) {
+  auto kern = tc_xprop_kernel<BS, BF16, OCC, VAR, 2>;
+  constexpr size_t smem = xprop_smem_bytes<BS, OCC, VAR>();
+  static thread_local uint64_t configured = 0;
+  if (int e = ensure_dyn_smem(kern, smem, configured)) return e;
+  p.counter = nullptr; p.order = nullptr;                 // clusters use the static deal over tile pairs
+  const int pairs = (p.n_ktiles / 2) * p.n_ntiles;
+  int clusters = sm_count * OCC / 2;
+  if (clusters > pairs) clusters = pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(xprop_threads<XpropCfg<BS, OCC, VAR>>()); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, maps);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "cluster launch: %s", cudaGetErrorString(e)); }
+  return check_launch("tcgen05_xprop_bs32_pair");
 }
 
 template <int BS, bool BF16, int OCC, int VAR = 0>
@@ -635,7 +678,8 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
   if (!p.counter && !static_tiles()) return fail(BSMM_E_NODEV, "bsmm_xprop: tile counters not available");
   p.order = (order_off > 0 && !static_order()) ? sched + order_off : nullptr;
   const int tile_blocks = sched_tile_blocks & 0xff;
-  const int w_per_group = sched_tile_blocks >> 8;          // 0 = the default of the tile width
+  const int w_per_group = (sched_tile_blocks >> 8) & 0xf;  // 0 = the default of the tile width
+  const bool pair_tiles = (sched_tile_blocks >> 12) & 1;   // schedule built with pair_tiles=True: cluster kernel
   const int occ = (tile_blocks * bsize <= 256) ? 2 : 1;      // half-width tiles run two CTAs per SM
   if (p.n_ktiles <= 0 || tile_blocks <= 0 || tile_blocks > 512 / bsize || (long long)p.n_ktiles * tile_blocks < n_out ||
       sched_groups_off < 4 + 4 * p.n_ktiles || (sched_groups_off & 31))
@@ -645,6 +689,12 @@ inline int tc_xprop(int dtype, int axis, int bsize, int bprop, const int32_t* lu
     if (occ != 2 || (w_per_group != 0 && w_per_group != 8))
       return fail(BSMM_E_ARG, "bsmm_xprop: 16 x 16 blocks need 16-block tiles and 8 W blocks per group");
     return dtype == BSMM_BF16 ? launch_tc_xprop<16, true, 2>(p, maps, dev.sm_grid, s) : launch_tc_xprop<16, false, 2>(p, maps, dev.sm_grid, s);
+  }
+  if (pair_tiles) {
+    if (!(occ == 2 && bsize == 32 && (w_per_group == 4 || w_per_group == 2)) || (p.n_ktiles & 1))
+      return fail(BSMM_E_ARG, "bsmm_xprop: pair-tile schedules need 32 x 32 blocks, 8-block tiles, 2 or 4 W blocks per group and an even tile count");
+    if (w_per_group == 4) return dtype == BSMM_BF16 ? launch_tc_xprop_pair<32, true, 2, 3>(p, maps, dev.sm_grid, s) : launch_tc_xprop_pair<32, false, 2, 3>(p, maps, dev.sm_grid, s);
+    return dtype == BSMM_BF16 ? launch_tc_xprop_pair<32, true, 2, 1>(p, maps, dev.sm_grid, s) : launch_tc_xprop_pair<32, false, 2, 1>(p, maps, dev.sm_grid, s);
   }
   if (occ == 2 && bsize == 32 && w_per_group == 4) {
     return dtype == BSMM_BF16 ? launch_tc_xprop<32, true, 2, 3>(p, maps, dev.sm_grid, s)

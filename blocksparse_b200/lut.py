@@ -171,6 +171,11 @@ class MatmulLuts(object):
         n_out = self.CB if bprop else self.KB
         return build_pair_schedule(outs, ins, wids, n_out, blocks_per_tile, w_per_group, n_tiles, n_ntiles, n_ctas, bsize)
 
+    def pair_tile_schedule(self, bprop, blocks_per_tile, bsize, w_per_group, n_tiles):
+        outs, ins, wids = self._b if bprop else self._f
+        n_out = self.CB if bprop else self.KB
+        return build_pair_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group, n_tiles)
+
     def tile_schedule(self, bprop, blocks_per_tile, bsize=32, w_per_group=8, n_tiles=None, n_ntiles=None):
         outs, ins, wids = self._b if bprop else self._f
         n_out = self.CB if bprop else self.KB
@@ -322,6 +327,83 @@ def build_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize=32, w_per
         order = tile_order(cost, int(n_ntiles))
         order_off = len(sched)
         return np.concatenate((sched, order)), grp_off, order_off
+    return sched, grp_off
+
+
+def build_pair_tile_schedule(outs, ins, wids, n_out, blocks_per_tile, bsize, w_per_group, n_tiles):
+    """build_tile_schedule for the 2-CTA cluster kernel (csrc/tc.cuh, CL = 2): output tiles 2P and 2P+1 walk ONE merged
+    group list, so that the activation tile of every group can be fetched once and multicast to both CTAs.
+
+    For every input block with a consumer in either tile of the pair both tiles get the same number of group records (the
+    larger of the two tiles' needs); a tile with nothing to multiply in a group gets a record with n_w = 0.  An odd tile
+    count is padded with an empty tile.  Same record / header layout as build_tile_schedule.
+    Returns (schedule, groups_offset); the tile count in schedule[0] is even.
+    """
+    T, WPG = int(blocks_per_tile), int(w_per_group)
+    assert 1 <= WPG <= GROUP_MAX_W
+    n_tiles = int(n_tiles)
+    assert n_tiles * T >= n_out
+    bounds = (np.arange(n_tiles + 1, dtype=np.int64) * n_out) // n_tiles
+    outs = np.asarray(outs, dtype=np.int64); ins = np.asarray(ins, dtype=np.int64); wids = np.asarray(wids, dtype=np.int64)
+    tile = np.searchsorted(bounds, outs, side="right") - 1
+    n_even = n_tiles + (n_tiles & 1)
+    wbytes16 = (bsize * bsize * 2) >> 4
+    max_run = 256 // bsize
+    # per tile: {in_block: [(slot, w), ...] sorted by slot}
+    per_tile = [dict() for _ in range(n_even)]
+    order = np.lexsort((outs, ins, tile))
+    for t, c, o, w in zip(tile[order].tolist(), ins[order].tolist(), outs[order].tolist(), wids[order].tolist()):
+        per_tile[t].setdefault(c, []).append((o - int(bounds[t]), w))
+    recs = [[] for _ in range(n_even)]
+
+    def records(entries, in_block, n_rec):
+        out = []
+        for r in range(n_rec):
+            chunk = entries[r * WPG:(r + 1) * WPG]
+            rec = [0] * GROUP_INTS
+            rec[0] = in_block
+            runs = []
+            for pos, (slot, w) in enumerate(chunk):
+                rec[4 + pos] = w
+                if runs and runs[-1][1] + runs[-1][2] == slot and runs[-1][2] < max_run:
+                    runs[-1][2] += 1
+                else:
+                    runs.append([pos, slot, 1])
+            assert len(runs) <= GROUP_MAX_RUNS
+            rec[1] = len(chunk) | (len(runs) << 8)
+            for i, (pos, slot, ln) in enumerate(runs):
+                rec[12 + i] = (pos * wbytes16) | ((slot * bsize) << 16)
+                rec[20 + i] = (((ln * bsize) >> 3) << 17) | 1
+            out.append(rec)
+        return out
+
+    for P in range(n_even // 2):
+        a, b = per_tile[2 * P], per_tile[2 * P + 1]
+        for c in sorted(set(a) | set(b)):
+            ea, eb = a.get(c, []), b.get(c, [])
+            n_rec = max(ceil_div(len(ea), WPG), ceil_div(len(eb), WPG), 1)
+            recs[2 * P] += records(ea, c, n_rec)
+            recs[2 * P + 1] += records(eb, c, n_rec)
+    groups_per_tile = np.array([len(r) for r in recs], dtype=np.int64)
+    tile_first_group = np.concatenate(([0], np.cumsum(groups_per_tile)[:-1]))
+    touched = np.zeros(n_even, dtype=np.int64)
+    np.bitwise_or.at(touched, tile, np.int64(1) << (outs - bounds[tile]))
+    hdr_ints = 4 + 4 * n_even
+    grp_off = ceil_div(hdr_ints, GROUP_INTS) * GROUP_INTS
+    n_groups = int(groups_per_tile.sum())
+    sched = np.zeros(grp_off + GROUP_INTS * n_groups, dtype=np.int32)
+    sched[0:4] = (n_even, T, n_groups, len(outs))
+    th = sched[4:hdr_ints].reshape(n_even, 4)
+    th[:, 0] = tile_first_group
+    th[:, 1] = groups_per_tile
+    th[:n_tiles, 2] = bounds[:-1]
+    th[:n_tiles, 3] = np.diff(bounds) | (touched[:n_tiles] << 8)
+    if n_even > n_tiles:                      # padding tile: no output blocks, only takes part in the barrier protocol
+        th[n_tiles, 2] = n_out
+        th[n_tiles, 3] = 0
+    flat = [r for tr in recs for r in tr]
+    if flat:
+        sched[grp_off:] = np.asarray(flat, dtype=np.int64).astype(np.int32).reshape(-1)
     return sched, grp_off
 
 

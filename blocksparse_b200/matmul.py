@@ -30,6 +30,8 @@ _SCHED_CACHE_MAX = 16
 # explain why), so 0 -- the default -- keeps csrc/tc.cuh.
 _X2_VARIANTS = {1: (8, 2, 4), 2: (8, 2, 8), 3: (16, 1, 12)}
 _X2_FORCE = int(os.environ.get("BSMM_XPROP2", "0"))
+# BSMM_PAIR_TILES=1: 32 x 32 blocks at <= ~37 % density run as 2-CTA clusters that multicast the activation tiles
+_PAIR_TILES = int(os.environ.get("BSMM_PAIR_TILES", "0"))
 _W_PER_GROUP = {16: 8, 32: 8, 64: 2 if _OCC[64] == 2 else 4}
 
 
@@ -246,14 +248,27 @@ class BlocksparseMatMul(MatmulCheckers):
                 # 1..3 W blocks per group on average (density <= 37.5 %): 4 W slots per stage, 6 stages in flight
                 wpg, sparse = 4, True
             n_nt = -(-N // 128)
-            key = (bool(bprop), n_kt, wpg, n_nt)
-            if key not in d["xprop_sched"]:
+            if sparse and self.bsize == 32 and _PAIR_TILES and x.dtype != torch.float32:
+                # 2-CTA clusters over neighbouring output tiles sharing every activation tile by TMA multicast (csrc/tc.cuh, CL = 2)
+                key = ("pairtile", bool(bprop), n_kt, wpg)
+                if key not in d["xprop_sched"]:
+                    arr, off = self._luts.pair_tile_schedule(bprop, tb, self.bsize, wpg, n_kt)
+                    while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:
+                        d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
+                    d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off, 0)
+                sched, sched_tiles, sched_off, list_off = d["xprop_sched"][key]
+                tile_arg = tb | (wpg << 8) | (1 << 12)
+                key = None
+            else:
+                key = (bool(bprop), n_kt, wpg, n_nt)
+            if key is not None and key not in d["xprop_sched"]:
                 arr, off, ooff = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt, n_ntiles=n_nt)
                 while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:       # bounded: one entry per distinct minibatch tile count
                     d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
                 d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off, ooff)
-            sched, sched_tiles, sched_off, list_off = d["xprop_sched"][key]
-            tile_arg = tb | ((wpg << 8) if sparse else 0)
+            if key is not None:
+                sched, sched_tiles, sched_off, list_off = d["xprop_sched"][key]
+                tile_arg = tb | ((wpg << 8) if sparse else 0)
         y2 = torch.empty((feat_out, N) if self.axis == 0 else (N, feat_out), dtype=x.dtype, device=x.device)
         if gate is not None:
             gate = gate.to(torch.float32).contiguous()
@@ -341,24 +356,26 @@ class BlocksparseMatMul(MatmulCheckers):
         """
         self.count += 1
         if bench:
-            self._bench_forward(I, W, gate, bench, name or self.name)
-        return _BsmmFunction.apply(I, W, gate, self, bool(gate_grad), bool(dw_gated))
+            self._bench_op("fprop", lambda: self.fprop(I, W, gate), I, bench, name or self.name)
+        return _BsmmFunction.apply(I, W, gate, self, bool(gate_grad), bool(dw_gated), int(bench), name or self.name)
 
-    def _bench_forward(self, I, W, gate, repeat, name):
+    def _bench_op(self, what, fn, I, repeat, name):
+        """The reference's `bench` attribute (op.cc:99-106,181-185, gpu_types.cc:43-87): repeat the launch `repeat` times
+        between two CUDA events and print one line; applies to fprop and, through the backward pass, to bprop and updat."""
         lib = _lib.load()
         timer = ctypes.c_void_p()
         _lib.check(lib.bsmm_timer_create(ctypes.byref(timer)), "timer_create")
-        self.fprop(I, W, gate)
+        fn()
         _lib.check(lib.bsmm_timer_begin(timer, _lib.stream_ptr()), "timer_begin")
         for _ in range(repeat):
-            self.fprop(I, W, gate)
+            fn()
         ms = ctypes.c_float()
         _lib.check(lib.bsmm_timer_end(timer, _lib.stream_ptr(), ctypes.byref(ms)), "timer_end")
         lib.bsmm_timer_destroy(timer)
-        N = I.numel() // self.C
+        N = I.numel() // (self.K if what == "bprop" else self.C)
         ms_per = ms.value / repeat
         gflops = self.flops * N / (ms_per * 1e6)
-        print("%s fprop ms: %.4f gflops: %.0f" % (name, ms_per, gflops))
+        print("%s %s ms: %.4f gflops: %.0f" % (name, what, ms_per, gflops))
         return ms_per
 
 
@@ -366,8 +383,8 @@ class _BsmmFunction(torch.autograd.Function):
     """Mirrors blocksparse_matmul_grad (reference matmul.py:485-527)."""
 
     @staticmethod
-    def forward(ctx, x, w, gate, bsmm, gate_grad, dw_gated):
-        ctx.bsmm, ctx.gate_grad, ctx.dw_gated = bsmm, gate_grad, dw_gated
+    def forward(ctx, x, w, gate, bsmm, gate_grad, dw_gated, bench=0, name=None):
+        ctx.bsmm, ctx.gate_grad, ctx.dw_gated, ctx.bench, ctx.name = bsmm, gate_grad, dw_gated, bench, name
         ctx.save_for_backward(x, w, gate)
         return bsmm.fprop(x, w, gate)
 
@@ -376,6 +393,9 @@ class _BsmmFunction(torch.autograd.Function):
         x, w, gate = ctx.saved_tensors
         bsmm = ctx.bsmm
         dy = dy.contiguous()
+        if ctx.bench:
+            bsmm._bench_op("bprop", lambda: bsmm.bprop(dy, w, gate), dy, ctx.bench, ctx.name)
+            bsmm._bench_op("updat", lambda: bsmm.updat([x], [dy], gate=gate, dw_gated=ctx.dw_gated), x, ctx.bench, ctx.name)
         dx = bsmm.bprop(dy, w, gate) if ctx.needs_input_grad[0] else None
         dw = dg = None
         want_dg = gate is not None and ctx.gate_grad and ctx.needs_input_grad[2]
@@ -391,7 +411,7 @@ class _BsmmFunction(torch.autograd.Function):
                 dw = pending.add(x, dy, gate, ctx.dw_gated)
             else:
                 dw = bsmm.updat([x], [dy], gate=gate, dw_gated=ctx.dw_gated)
-        return dx, dw, dg, None, None, None
+        return dx, dw, dg, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------

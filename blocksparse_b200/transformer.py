@@ -172,22 +172,47 @@ class BlocksparseTransformer(TransformerCheckers):
         return out
 
     # ------------------------------------------------------------------ public ops (autograd)
+    def _bench(self, what, fn, a, hs, repeat, name):
+        """The reference's `bench` op attribute (transformer.py:166-181, src/bst_op.cc:160-176,221-222): time `repeat`
+        launches between two CUDA events and print one line."""
+        import ctypes
+        lib = _lib.load()
+        timer = ctypes.c_void_p()
+        _lib.check(lib.bsmm_timer_create(ctypes.byref(timer)), "timer_create")
+        fn()
+        _lib.check(lib.bsmm_timer_begin(timer, _lib.stream_ptr()), "timer_begin")
+        for _ in range(repeat):
+            fn()
+        ms = ctypes.c_float()
+        _lib.check(lib.bsmm_timer_end(timer, _lib.stream_ptr(), ctypes.byref(ms)), "timer_end")
+        lib.bsmm_timer_destroy(timer)
+        ms_per = ms.value / repeat
+        flops = 2.0 * self.blocks * self.blk_size * self.blk_size * hs * a.shape[0] * self.heads
+        print("%s %s ms: %.4f gflops: %.0f" % (name or self.name or "bst", what, ms_per, flops / (ms_per * 1e6)))
+        return ms_per
+
     def nt_op(self, a, b, name=None, bench=0):
+        if bench:
+            self._bench("nt", lambda: self._nt(a, b, torch.bfloat16), a, a.shape[2] // self.heads, bench, name)
         return _NtFunction.apply(a, b, self, torch.bfloat16)
 
     def nn_op(self, a, b, name=None, bench=0):
+        if bench:
+            self._bench("nn", lambda: self._xn(a, b, False), b, b.shape[2] // self.heads, bench, name)
         return _XnFunction.apply(a, b, self, False)
 
     def tn_op(self, a, b, name=None, bench=0):
+        if bench:
+            self._bench("tn", lambda: self._xn(a, b, True), b, b.shape[2] // self.heads, bench, name)
         return _XnFunction.apply(a, b, self, True)
 
     def query_key_op(self, q, k, name=None, bench=0):
         # reference transformer.py:337-347: scores are always bf16; softmax output dtype follows q
         self.softmax_dtype = torch.bfloat16 if q.dtype == torch.float32 else q.dtype
-        return _NtFunction.apply(q, k, self, torch.bfloat16)
+        return self.nt_op(q, k, name=name, bench=bench)
 
     def weight_value_op(self, w, v, name=None, bench=0):
-        return _XnFunction.apply(w, v, self, False)
+        return self.nn_op(w, v, name=name, bench=bench)
 
     def masked_softmax(self, x, scale=1.0, autoregress_at_key=None, dtype=None):
         if self.softmax_mask_np is None:

@@ -72,3 +72,46 @@ def test_lpt_lists_balance_a_skewed_cost_vector():
     assert max(load) <= 1.05 * (cost.sum() * 4 / 8) or max(load) == 100.0 + min(load) - min(load)   # near the mean
     assert max(load) - min(load) <= 100.0
     assert sorted(ids.tolist()) == list(range(4 * 31))
+
+
+@pytest.mark.parametrize("bprop", [False, True])
+@pytest.mark.parametrize("shape,density,n_kt,wpg", [((33, 40), 0.1, 5, 2), ((64, 64), 0.3, 8, 4), ((7, 20), 1.0, 3, 4), ((128, 128), 0.25, 18, 4)])
+def test_pair_tile_schedule_pairs_walk_one_group_list(shape, density, n_kt, wpg, bprop):
+    """build_pair_tile_schedule: tiles 2P and 2P+1 have the same number of groups with the same input blocks in the same
+    order, every LUT entry is multiplied exactly once, and an odd tile count is padded with an empty tile."""
+    from blocksparse_b200.lut import MatmulLuts
+    rng = np.random.default_rng(sum(shape) + n_kt)
+    lay = (rng.random(shape) < density).astype(np.int32)
+    lay[0, 0] = 1
+    luts = MatmulLuts(lay)
+    n_out = shape[0] if bprop else shape[1]
+    n_kt = min(n_kt, n_out)
+    if -(-n_out // n_kt) > 8:
+        n_kt = -(-n_out // 8)
+    sched, goff = luts.pair_tile_schedule(bprop, 8, 32, wpg, n_kt)
+    n_tiles = int(sched[0])
+    assert n_tiles % 2 == 0 and n_tiles in (n_kt, n_kt + 1)
+    th = sched[4:4 + 4 * n_tiles].reshape(n_tiles, 4)
+    recs = sched[goff:].reshape(-1, 32)
+    triples = []
+    for P in range(n_tiles // 2):
+        fa, na = th[2 * P][:2]; fb, nb = th[2 * P + 1][:2]
+        assert na == nb
+        assert np.array_equal(recs[fa:fa + na, 0], recs[fb:fb + nb, 0])          # same input block sequence
+        assert np.all(np.diff(recs[fa:fa + na, 0]) >= 0)
+    for t in range(n_tiles):
+        first, n_g, out0, packed = th[t]
+        for rec in recs[first:first + n_g]:
+            n_w, n_runs = rec[1] & 0xff, rec[1] >> 8
+            assert n_w <= wpg
+            covered = 0
+            for r in range(n_runs):
+                pos = (rec[12 + r] & 0xffff) // 128
+                col = rec[12 + r] >> 16
+                nblk = ((rec[20 + r] >> 17) << 3) // 32
+                for i in range(nblk):
+                    triples.append((int(out0) + col // 32 + i, int(rec[0]), int(rec[4 + pos + i])))
+                covered += nblk
+            assert covered == n_w
+    outs, ins, wids = luts._b if bprop else luts._f
+    assert sorted(triples) == sorted(zip(outs.tolist(), ins.tolist(), wids.tolist()))

@@ -308,3 +308,33 @@ def test_cuda_graph_capture_and_replay():
     torch.cuda.synchronize()
     assert torch.equal(y, bsmm.fprop(X, W))
     assert _lib.device_error() == 0
+
+
+@pytest.mark.parametrize("axis", [1, 0])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", [(8, 8, 0.3, 128), (40, 33, 0.08, 1), (64, 64, 0.2, 640), (9, 47, 0.3, 200), (128, 128, 0.25, 1024)])
+def test_tc_xprop_pair_tiles_match_oracle(case, dtype, axis, monkeypatch):
+    """2-CTA clusters sharing every activation tile by TMA multicast (BSMM_PAIR_TILES, csrc/tc.cuh CL = 2): same results, bit for
+    bit, as the single-CTA kernel (each output tile still sees its MMAs in ascending input-block order)."""
+    import blocksparse_b200.matmul as mm
+    CB, KB, density, N = case
+    if axis == 0:
+        N = max(8, (N + 7) // 8 * 8)
+    rng = np.random.default_rng(CB * 1000 + KB * 10 + N)
+    lay = layout(rng, CB, KB, density, empty_col=KB // 2, empty_row=1)
+    W = torch.as_tensor(rng.normal(0, 0.1, (int(lay.sum()), 32, 32)).astype(np.float32)).to(dtype).cuda()
+    res = {}
+    for pair in (0, 1):
+        monkeypatch.setattr(mm, "_PAIR_TILES", pair)
+        bsmm = BlocksparseMatMul(lay, block_size=32, feature_axis=axis)
+        X = torch.as_tensor(np.random.default_rng(1).normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).to(dtype).cuda()
+        E = torch.as_tensor(np.random.default_rng(2).normal(0, 1, bsmm.o_shape(N)).astype(np.float32)).to(dtype).cuda()
+        y = bsmm.fprop(X, W, flags=_lib.FLAG_FORCE_TC); k1 = _lib.last_kernel()
+        dx = bsmm.bprop(E, W, flags=_lib.FLAG_FORCE_TC); k2 = _lib.last_kernel()
+        assert _lib.device_error() == 0, _lib.device_error_text()
+        assert k1 == k2 == ("tcgen05_xprop_bs32_pair" if pair else "tcgen05_xprop_bs32"), (k1, k2)
+        res[pair] = (y, dx)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    orc = MatmulOracle(lay, 32, axis)
+    mx, l2 = ref_errors(res[1][0].float().cpu().numpy(), orc.fprop_dense(X.float().cpu().numpy(), W.float().cpu().numpy()))
+    assert l2 <= (4e-3 if dtype == torch.bfloat16 else 1e-3), "pair-tile fprop l2 %.3e" % l2
