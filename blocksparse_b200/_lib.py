@@ -45,6 +45,8 @@ SIGNATURES = {
     "bsmm_reduced_dw_workspace_bytes": (_c.c_size_t, [_i, _i]),
     "bsmm_reduced_dw": (_i, [_i, _i, _i, _c.POINTER(_vp), _c.POINTER(_vp), _i, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "bsmm_gather_rows": (_i, [_i, _vp, _vp, _vp, _vp, _i, _c.c_longlong, _i, _vp]),
+    "bsmm_pad_blocks": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "bsmm_unpad_blocks": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "bsmm_timer_create": (_i, [_c.POINTER(_vp)]),
     "bsmm_timer_begin": (_i, [_vp, _vp]),
     "bsmm_timer_end": (_i, [_vp, _vp, _c.POINTER(_f)]),

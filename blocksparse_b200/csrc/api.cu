@@ -501,4 +501,24 @@ int bsmm_gather_rows(int dtype, const void* x, const void* y, const int32_t* idx
   });
   return check_launch("gather_rows");
 }
+
+int bsmm_pad_blocks(int dtype, int bsize, int blocks_big, const int32_t* sub_map, const void* w_small, const float* gate, void* w_big, void* stream) {
+  if (!sub_map || !w_small || !w_big || blocks_big <= 0 || (bsize != 8 && bsize != 16 && bsize != 32)) return fail(BSMM_E_ARG, "bsmm_pad_blocks: bad arguments");
+  BSMM_DISPATCH_DTYPE(dtype, T, {
+    pad_blocks_kernel<T><<<blocks_big, 128, 0, (cudaStream_t)stream>>>((const T*)w_small, sub_map, gate, (T*)w_big, blocks_big, bsize);
+  });
+  return check_launch("pad_blocks");
+}
+
+int bsmm_unpad_blocks(int in_dtype, int out_dtype, int bsize, int blocks_small, const int32_t* inv_map, const void* dw_big, const float* gate,
+                      void* dw_small, int accumulate, void* stream) {
+  if (!inv_map || !dw_big || !dw_small || blocks_small <= 0 || (bsize != 8 && bsize != 16 && bsize != 32)) return fail(BSMM_E_ARG, "bsmm_unpad_blocks: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  BSMM_DISPATCH_DTYPE(in_dtype, TI, {
+    BSMM_DISPATCH_DTYPE(out_dtype, TO, {
+      unpad_blocks_kernel<TI, TO><<<blocks_small, 64, 0, s>>>((const TI*)dw_big, inv_map, gate, (TO*)dw_small, blocks_small, bsize, accumulate);
+    });
+  });
+  return check_launch("unpad_blocks");
+}
 }  // extern "C"

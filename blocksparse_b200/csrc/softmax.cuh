@@ -235,7 +235,7 @@ constexpr int SOFTMAX_STAGED_THREADS = 128;
 constexpr int SOFTMAX_STAGED_ROWS = 16;
 
 template <typename TX, typename TY, int BS, int MAXE>
-__global__ void __launch_bounds__(SOFTMAX_STAGED_THREADS)
+__global__ void __launch_bounds__(SOFTMAX_STAGED_THREADS, 8)      // <= 64 registers: eight CTAs (~180 KB of chunks) in flight per SM
 bst_softmax_staged_kernel(const SoftmaxParams p) {
   static_assert(sizeof(TX) == 2 && sizeof(TY) == 2 && (BS == 32 || BS == 64), "staged softmax: 16-bit, bs 32/64");
   using MT = typename MaskWord<BS>::type;
@@ -245,6 +245,7 @@ bst_softmax_staged_kernel(const SoftmaxParams p) {
   extern __shared__ __align__(128) uint8_t sm_blocks[];
   __shared__ uint64_t bar;
   __shared__ int2 s_ent[MAXE];
+  __shared__ uint64_t s_mask[MAXE][RC];           // mask word of every (block, row) of the chunk, fetched while the tiles fly
   const int q = blockIdx.x / NCH, row0 = (blockIdx.x % NCH) * RC, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int hl = p.nn_head_stride ? h : 0;
@@ -268,15 +269,25 @@ bst_softmax_staged_kernel(const SoftmaxParams p) {
                    ::"r"((uint32_t)__cvta_generic_to_shared(sm_blocks + (size_t)e * BLK_BYTES)), "l"(src), "r"(BLK_BYTES), "r"(bar_a) : "memory");
     }
   }
+  const MT* mask = reinterpret_cast<const MT*>(p.mask);
+  if (mask) {
+    mask += (p.mask_head_stride ? (long long)h * p.mask_head_stride : 0);
+    for (int i = tid; i < count * RC; i += SOFTMAX_STAGED_THREADS) {
+      const int e = i / RC, r = i % RC;
+      uint64_t w = (uint64_t)mask[(long long)s_ent[e].x * BS + row0 + r];
+      if (p.autoregress_at_key >= 0) w = autoregress_word<BS>(w, p.autoregress_at_key, s_ent[e].y, q * BS + row0 + r);
+      s_mask[e][r] = w;
+    }
+    __syncthreads();
+  }
   {   // every thread waits for the data (parity 0: single use of the barrier)
     uint32_t ok = 0;
     while (!ok)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok) : "r"(bar_a) : "memory");
   }
-  const MT* mask = reinterpret_cast<const MT*>(p.mask);
-  if (mask) mask += (p.mask_head_stride ? (long long)h * p.mask_head_stride : 0);
   constexpr float LOG2E = 1.4426950408889634f;
+  constexpr uint64_t ALL = (BS == 64) ? ~0ull : ((1ull << BS) - 1ull);
   const float sc2 = p.scale * LOG2E;              // work in the exp2 domain: v = x * scale * log2(e)
   for (int lr = warp; lr < RC; lr += SOFTMAX_STAGED_THREADS / 32) {
     const int row = row0 + lr;
@@ -289,10 +300,11 @@ bst_softmax_staged_kernel(const SoftmaxParams p) {
         if constexpr (EPL == 2) { const float2 t = load2<TX>(src); v[e][0] = t.x * sc2; v[e][1] = t.y * sc2; }
         else v[e][0] = to_f32<TX>(*src) * sc2;
         if (mask) {
-          uint64_t w = (uint64_t)mask[(long long)s_ent[e].x * BS + row];
-          if (p.autoregress_at_key >= 0) w = autoregress_word<BS>(w, p.autoregress_at_key, s_ent[e].y, q * BS + row);
+          const uint64_t w = s_mask[e][lr];                 // warp-uniform; most blocks are fully visible: skip the bit tests
+          if (w != ALL) {
 #pragma unroll
-          for (int i = 0; i < EPL; ++i) if (!((w >> (lane * EPL + i)) & 1ull)) v[e][i] = -FLT_MAX;
+            for (int i = 0; i < EPL; ++i) if (!((w >> (lane * EPL + i)) & 1ull)) v[e][i] = -FLT_MAX;
+          }
         }
 #pragma unroll
         for (int i = 0; i < EPL; ++i) m = fmaxf(m, v[e][i]);

@@ -241,4 +241,43 @@ __global__ void gather_rows_kernel(const T* __restrict__ x, const T* __restrict_
   }
 }
 
+// ---- 8 x 8 blocks on the tensor cores: pad 2 x 2 neighbourhoods into 16 x 16 blocks ---------------------------------
+// tcgen05.mma needs N >= 16, so an 8 x 8 block cannot be a B operand on its own.  The host layer builds a SHADOW layout of
+// 16 x 16 super-blocks (one per 2 x 2 neighbourhood that holds at least one 8 x 8 block), these kernels scatter the weights
+// into it (absent sub-blocks are zero, the optional gate is folded in) and gather the weight gradient back out.  The padded
+// product multiplies zeros -- at 20 % density about a third of the super-block is real -- but runs ~10x faster than the
+// CUDA-core FMA kernels (profiles/r2_bench_cfg4.jsonl).
+template <typename T>
+__global__ void pad_blocks_kernel(const T* __restrict__ w_small, const int32_t* __restrict__ sub_map, const float* __restrict__ gate,
+                                  T* __restrict__ w_big, int blocks_big, int bs) {
+  const int B = 2 * bs, n = B * B;
+  const int b = blockIdx.x;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int i = idx / B, j = idx % B;
+    const int src = sub_map[4 * b + (i / bs) * 2 + (j / bs)];
+    float v = 0.f;
+    if (src >= 0) {
+      v = to_f32(w_small[((size_t)src * bs + (i % bs)) * bs + (j % bs)]);
+      if (gate) v *= gate[src];
+    }
+    w_big[(size_t)b * n + idx] = from_f32<T>(v);
+  }
+}
+// inv_map[w] = super-block id * 4 + sub-position
+template <typename TI, typename TO>
+__global__ void unpad_blocks_kernel(const TI* __restrict__ dw_big, const int32_t* __restrict__ inv_map, const float* __restrict__ gate,
+                                    TO* __restrict__ dw_small, int blocks_small, int bs, int accumulate) {
+  const int B = 2 * bs;
+  const int w = blockIdx.x;
+  const int m = inv_map[w], big = m >> 2, sub = m & 3;
+  const TI* src = dw_big + (size_t)big * B * B + (size_t)(sub >> 1) * bs * B + (sub & 1) * bs;
+  for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
+    const int i = idx / bs, j = idx % bs;
+    float v = to_f32(src[i * B + j]);
+    if (gate) v *= gate[w];                        // gated dW (reference op.cc:274), applied before the output rounding
+    if (accumulate) v += to_f32(dw_small[(size_t)w * bs * bs + idx]);
+    dw_small[(size_t)w * bs * bs + idx] = from_f32<TO>(v);
+  }
+}
+
 }  // namespace bsmm

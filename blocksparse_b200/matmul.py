@@ -32,6 +32,8 @@ _X2_VARIANTS = {1: (8, 2, 4), 2: (8, 2, 8), 3: (16, 1, 12)}
 _X2_FORCE = int(os.environ.get("BSMM_XPROP2", "0"))
 # BSMM_PAIR_TILES=1: 32 x 32 blocks at <= ~37 % density run as 2-CTA clusters that multicast the activation tiles
 _PAIR_TILES = int(os.environ.get("BSMM_PAIR_TILES", "0"))
+# BSMM_PAD8=0: keep 8 x 8 blocks on the CUDA-core FMA kernels instead of the padded 16 x 16 tcgen05 path
+_PAD8 = int(os.environ.get("BSMM_PAD8", "1"))
 _W_PER_GROUP = {16: 8, 32: 8, 64: 2 if _OCC[64] == 2 else 4}
 
 
@@ -83,6 +85,19 @@ class BlocksparseMatMul(MatmulCheckers):
         self.sparsity = round(float(self.blocks) / float(self.CB * self.KB), 3)
         self.layout = layout != 0
         self._dev = {}          # device -> dict of LUT tensors (uploaded once, matmul.py:33-53)
+        # 8 x 8 blocks: tcgen05.mma needs N >= 16, so 16-bit dtypes run on a SHADOW op over 16 x 16 super-blocks (2 x 2
+        # neighbourhoods, absent sub-blocks zero) fed through bsmm_pad_blocks / bsmm_unpad_blocks (csrc/wutil.cuh)
+        self._shadow = None
+        if block_size == 8 and _PAD8 and self.CB % 2 == 0 and self.KB % 2 == 0:
+            big = self.layout.reshape(self.CB // 2, 2, self.KB // 2, 2).any(axis=(1, 3))
+            sh = BlocksparseMatMul(big.astype(np.int32), block_size=16, feature_axis=feature_axis, z_order=z_order, name=self.name + "/pad16")
+            big_id = -np.ones(big.shape, dtype=np.int64)
+            big_id[sh.updat_lut[:, 0], sh.updat_lut[:, 1]] = np.arange(sh.blocks)
+            cs, ks = self.updat_lut[:, 0].astype(np.int64), self.updat_lut[:, 1].astype(np.int64)
+            inv = big_id[cs // 2, ks // 2] * 4 + (cs % 2) * 2 + (ks % 2)
+            sub = -np.ones(sh.blocks * 4, dtype=np.int32)
+            sub[inv] = np.arange(self.blocks, dtype=np.int32)
+            self._shadow, self._sub_map, self._inv_map = sh, sub, inv.astype(np.int32)
 
     def i_shape(self, N):
         return (N, self.C) if self.axis else (self.C, N)
@@ -200,11 +215,32 @@ class BlocksparseMatMul(MatmulCheckers):
     def bprop(self, dy, w, gate=None, flags=0):
         return self._xprop(dy, w, True, gate, flags)
 
+    def _pad_maps(self, device):
+        d = self._device_luts(device)
+        if "sub_map" not in d:
+            d["sub_map"] = torch.as_tensor(self._sub_map, device=device)
+            d["inv_map"] = torch.as_tensor(self._inv_map, device=device)
+        return d["sub_map"], d["inv_map"]
+
+    def _padded_weights(self, w, gate):
+        """(blocks, 8, 8) -> the shadow op's (blocks16, 16, 16), gate folded in."""
+        sub, _ = self._pad_maps(w.device)
+        sh = self._shadow
+        w16 = torch.empty(sh.w_shape, dtype=w.dtype, device=w.device)
+        g = None if gate is None else gate.to(torch.float32).contiguous()
+        _lib.check(_lib.load().bsmm_pad_blocks(_lib.dtype_code(w.dtype), self.bsize, sh.blocks, sub.data_ptr(), w.contiguous().data_ptr(),
+                                               _lib.ptr(g), w16.data_ptr(), _lib.stream_ptr()), "bsmm_pad_blocks")
+        return w16
+
     @_lib.guarded
     def _xprop(self, x, w, bprop, gate, flags):
         lib = _lib.load()
         if not x.is_cuda:
             raise _lib.BsmmError("BlocksparseMatMul needs CUDA tensors (no CPU path)")
+        if self._shadow is not None and x.dtype != torch.float32 and not (flags & _lib.FLAG_FORCE_GENERIC):
+            if tuple(w.shape) != self.w_shape or w.dtype != x.dtype:
+                raise ValueError("w must have shape %s and the dtype of x" % (self.w_shape,))
+            return self._shadow._xprop(x, self._padded_weights(w, gate), bprop, None, flags)
         feat_in, feat_out = (self.K, self.C) if bprop else (self.C, self.K)
         n_in, n_out = (self.KB, self.CB) if bprop else (self.CB, self.KB)
         x2 = _as_2d(x, self.axis, feat_in).contiguous()
@@ -310,6 +346,19 @@ class BlocksparseMatMul(MatmulCheckers):
                 raise ValueError("all x / dy tensors must share one dtype")
             if (a.shape[1] if self.axis == 0 else a.shape[0]) != N or (b.shape[1] if self.axis == 0 else b.shape[0]) != N:
                 raise ValueError("all x / dy tensors must share the minibatch size")
+        if self._shadow is not None and x0.dtype != torch.float32 and not (flags & _lib.FLAG_FORCE_GENERIC):
+            # 8 x 8 blocks: the padded 16 x 16 product in fp32, then gather this layout's blocks (alpha / gate / accumulate here)
+            dw16 = self._shadow.updat(xs, dys, alpha=alpha, dw_dtype=torch.float32, flags=flags)
+            _, inv = self._pad_maps(x0.device)
+            acc = dw is not None
+            if dw is None:
+                dw = torch.empty(self.w_shape, dtype=dw_dtype or x0.dtype, device=x0.device)
+            elif tuple(dw.shape) != self.w_shape or not dw.is_contiguous():
+                raise ValueError("dw must be a contiguous tensor of shape %s" % (self.w_shape,))
+            g = gate.to(torch.float32).contiguous() if (gate is not None and dw_gated) else None
+            _lib.check(lib.bsmm_unpad_blocks(_lib.F32, _lib.dtype_code(dw.dtype), self.bsize, self.blocks, inv.data_ptr(), dw16.data_ptr(),
+                                             _lib.ptr(g), dw.data_ptr(), int(acc), _lib.stream_ptr()), "bsmm_unpad_blocks")
+            return dw
         if dw is None:
             out_dtype = dw_dtype or x0.dtype
             dw = torch.empty(self.w_shape, dtype=out_dtype, device=x0.device)

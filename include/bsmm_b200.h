@@ -249,6 +249,14 @@ int bsmm_reduced_dw(int dtype, int axis, int bsize, const void* const* xs, const
  * op 1: out[r] = x[r] + (idx[r] >= 0 ? y[idx[r]] : 0);  op 2: out[r] = x[r] * (idx[r] >= 0 ? y[idx[r]] : 1). */
 int bsmm_gather_rows(int dtype, const void* x, const void* y, const int32_t* idx, void* out, int rows, long long N, int op, void* stream);
 
+/* 8 x 8 blocks on tcgen05 (N >= 16 per MMA): scatter a (blocks_small, bs, bs) weight tensor into (blocks_big, 2bs, 2bs)
+ * super-blocks -- sub_map[4*b + 2*(row half) + (col half)] = small block id or -1 (zero fill), optional per-small-block gate
+ * folded in -- and gather the weight gradient back: inv_map[w] = 4 * super-block + sub-position, optional per-block gate
+ * (gated dW), accumulate adds to dw_small. */
+int bsmm_pad_blocks(int dtype, int bsize, int blocks_big, const int32_t* sub_map, const void* w_small, const float* gate, void* w_big, void* stream);
+int bsmm_unpad_blocks(int in_dtype, int out_dtype, int bsize, int blocks_small, const int32_t* inv_map, const void* dw_big, const float* gate,
+                      void* dw_small, int accumulate, void* stream);
+
 /* ---- measurement helper (the reference's `bench` op attribute, op.cc:99-106) ---------
  * Records two events around whatever the caller enqueues between begin and end.      */
 int bsmm_timer_create(void** timer);

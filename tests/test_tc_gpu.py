@@ -338,3 +338,45 @@ def test_tc_xprop_pair_tiles_match_oracle(case, dtype, axis, monkeypatch):
     orc = MatmulOracle(lay, 32, axis)
     mx, l2 = ref_errors(res[1][0].float().cpu().numpy(), orc.fprop_dense(X.float().cpu().numpy(), W.float().cpu().numpy()))
     assert l2 <= (4e-3 if dtype == torch.bfloat16 else 1e-3), "pair-tile fprop l2 %.3e" % l2
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_bs8_runs_padded_on_tcgen05(dtype, axis):
+    """8 x 8 blocks: 2 x 2 neighbourhoods padded into 16 x 16 super-blocks (csrc/wutil.cuh pad/unpad) and run by the tcgen05
+    kernels; fprop / bprop / updat (alpha, accumulate, gate) against the oracle and against the CUDA-core path."""
+    rng = np.random.default_rng(8 + axis)
+    lay = layout(rng, 20, 14, 0.3, empty_col=3, empty_row=5)
+    bsmm = BlocksparseMatMul(lay, block_size=8, feature_axis=axis)
+    assert bsmm._shadow is not None and bsmm._shadow.bsize == 16
+    orc = MatmulOracle(lay, 8, 0)
+    orc.axis = axis
+    N = 136
+    W = torch.as_tensor(rng.normal(0, 0.2, bsmm.w_shape).astype(np.float32)).to(dtype)
+    X = torch.as_tensor(rng.normal(0, 1, bsmm.i_shape(N)).astype(np.float32)).to(dtype)
+    E = torch.as_tensor(rng.normal(0, 1, bsmm.o_shape(N)).astype(np.float32)).to(dtype)
+    Wn, Xn, En = W.float().numpy(), X.float().numpy(), E.float().numpy()
+    gate = (rng.random(bsmm.blocks) < 0.7).astype(np.float32) * 1.5
+    g = torch.as_tensor(gate).cuda()
+    tol = 4e-3 if dtype == torch.bfloat16 else 1e-3
+    for name, got, ref in [("fprop", bsmm.fprop(X.cuda(), W.cuda()), orc.fprop_dense(Xn, Wn)),
+                           ("bprop", bsmm.bprop(E.cuda(), W.cuda()), orc.bprop_dense(En, Wn)),
+                           ("fprop gated", bsmm.fprop(X.cuda(), W.cuda(), gate=g), orc.fprop_dense(Xn, Wn * gate[:, None, None]))]:
+        assert _lib.last_kernel() == "tcgen05_xprop_bs16", _lib.last_kernel()
+        mx, l2 = ref_errors(got.float().cpu().numpy(), ref)
+        assert l2 <= tol, "%s l2 %.3e" % (name, l2)
+    ref_dw = orc.updat_dense(Xn, En)
+    dw = bsmm.updat([X.cuda()], [E.cuda()], dw_dtype=torch.float32)
+    assert _lib.last_kernel() == "unpad_blocks"
+    mx, l2 = ref_errors(dw.cpu().numpy(), ref_dw)
+    assert l2 <= 1e-5, "updat l2 %.3e" % l2
+    bsmm.updat([X.cuda()], [E.cuda()], dw=dw, alpha=0.5)                           # in-place accumulate
+    mx, l2 = ref_errors(dw.cpu().numpy(), 1.5 * ref_dw)
+    assert l2 <= 1e-5, "accumulate l2 %.3e" % l2
+    dwg = bsmm.updat([X.cuda()], [E.cuda()], gate=g, dw_gated=True, dw_dtype=torch.float32)
+    mx, l2 = ref_errors(dwg.cpu().numpy(), ref_dw * gate[:, None, None])
+    assert l2 <= 1e-5
+    fma = bsmm.fprop(X.cuda(), W.cuda(), flags=_lib.FLAG_FORCE_GENERIC)
+    assert _lib.last_kernel().startswith("fma_")
+    assert (fma.float() - bsmm.fprop(X.cuda(), W.cuda()).float()).abs().max().item() <= 2.0 ** -7 * fma.float().abs().max().item()
+    assert _lib.device_error() == 0
