@@ -104,10 +104,16 @@ def last_kernel():
     return load().bsmm_last_kernel().decode()
 
 
+_DTYPE_CODES = None
+
+
 def dtype_code(torch_dtype):
-    import torch
+    global _DTYPE_CODES
+    if _DTYPE_CODES is None:
+        import torch
+        _DTYPE_CODES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
     try:
-        return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[torch_dtype]
+        return _DTYPE_CODES[torch_dtype]
     except KeyError:
         raise ValueError("unsupported dtype %s (float32, float16, bfloat16 only)" % (torch_dtype,))
 
@@ -116,39 +122,56 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_torch_cuda = None
+
+
 def stream_ptr():
-    import torch
-    return torch.cuda.current_stream().cuda_stream
+    global _torch_cuda
+    if _torch_cuda is None:
+        import torch
+        _torch_cuda = torch.cuda
+    return _torch_cuda.current_stream().cuda_stream
 
 
-def _iter_tensors(objs):
-    import torch
-    for o in objs:
-        if torch.is_tensor(o):
-            yield o
-        elif isinstance(o, (list, tuple)):
-            for t in _iter_tensors(o):
-                yield t
+_PTR_ARRAYS = {}
+
+
+def ptr_array(tensors):
+    """ctypes array of the tensors' data pointers (array types are cached: creating one costs ~10 us)."""
+    n = len(tensors)
+    t = _PTR_ARRAYS.get(n)
+    if t is None:
+        t = _PTR_ARRAYS[n] = ctypes.c_void_p * n
+    return t(*[x.data_ptr() for x in tensors])
 
 
 def guarded(fn):
     """Decorator for the raw ops: every CUDA operand must live on ONE device, and the call runs with that device
     current -- kernels launch on torch's current stream of the current device, and device properties, grid sizes and
     the tensor-map context come from cudaGetDevice, so an op on cuda:1 tensors while cuda:0 is current would otherwise
-    launch on the wrong GPU."""
+    launch on the wrong GPU.  (Written flat: it sits on the per-launch path.)"""
     import functools
+    import torch
+    is_tensor, cur = torch.is_tensor, torch.cuda.current_device
 
     @functools.wraps(fn)
     def wrapper(self, *args, **kw):
-        import torch
         dev = None
-        for t in _iter_tensors(list(args) + list(kw.values())):
-            if t.is_cuda:
-                if dev is None:
-                    dev = t.device
-                elif t.device != dev:
-                    raise ValueError("%s: operands live on different devices (%s and %s)" % (fn.__name__, dev, t.device))
-        if dev is None or torch.cuda.current_device() == dev.index:
+        for a in args:
+            if is_tensor(a):
+                if a.is_cuda:
+                    if dev is None:
+                        dev = a.device
+                    elif a.device != dev:
+                        raise ValueError("%s: operands live on different devices (%s and %s)" % (fn.__name__, dev, a.device))
+            elif type(a) in (list, tuple):
+                for t in a:
+                    if is_tensor(t) and t.is_cuda:
+                        if dev is None:
+                            dev = t.device
+                        elif t.device != dev:
+                            raise ValueError("%s: operands live on different devices (%s and %s)" % (fn.__name__, dev, t.device))
+        if dev is None or cur() == dev.index:
             return fn(self, *args, **kw)
         with torch.cuda.device(dev):
             return fn(self, *args, **kw)
