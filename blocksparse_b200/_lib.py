@@ -72,6 +72,12 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the symbol is missing
             fn.restype, fn.argtypes = res, args
         _lib = lib
+        # BSMM_WAIT_TIMEOUT_MS=<ms>[,notrap]: bound of the in-kernel barrier waits (compute-sanitizer / debuggers slow kernels
+        # down by orders of magnitude; the default is 2000 ms, then trap)
+        spec = os.environ.get("BSMM_WAIT_TIMEOUT_MS")
+        if spec:
+            parts = spec.split(",")
+            lib.bsmm_set_wait_timeout_ms(int(parts[0]), 0 if len(parts) > 1 and parts[1] == "notrap" else 1)
     return _lib
 
 

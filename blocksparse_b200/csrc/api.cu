@@ -53,6 +53,16 @@ int bsmm_set_wait_timeout_ms(int ms, int trap) {
 }
 
 // ---------------------------------------------------------------------------------------
+// A 16-bit call that cannot take the tcgen05 kernel runs ~25x slower on the CUDA-core path: say so once per process (the
+// reason is whatever tc_* recorded), unless BSMM_QUIET is set.  fp32 calls are expected there and stay silent.
+static void note_fallback(const char* op, int dtype) {
+  static std::atomic<bool> warned{false};
+  if (dtype == BSMM_F32 || warned.exchange(true)) return;
+  if (getenv("BSMM_QUIET")) return;
+  fprintf(stderr, "[bsmm_b200] %s: no tensor-core kernel for this call (%s); using the CUDA-core FMA kernel (about 25x slower). "
+                  "This message is printed once.\n", op, err_buf());
+}
+
 static int check_bsize_axis(int bsize, int axis) {
   if (axis != 0 && axis != 1) return fail(BSMM_E_BSIZE, "feature axis must be 0 or 1, got %d", axis);
   if (bsize != 8 && bsize != 16 && bsize != 32 && bsize != 64)
@@ -86,6 +96,7 @@ int bsmm_xprop(int dtype, int axis, int bsize, int bprop,
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC)
       return fail(BSMM_E_ARG, "bsmm_xprop: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());
+    note_fallback("bsmm_xprop", dtype);
   } else if (flags & BSMM_FLAG_FORCE_TC) {
     return fail(BSMM_E_ARG, "bsmm_xprop: contradictory flags");
   }
@@ -129,6 +140,7 @@ int bsmm_updat(int dtype, int dw_dtype, int axis, int bsize,
     if (rc != TC_NOT_APPLICABLE) return rc;
     if (flags & BSMM_FLAG_FORCE_TC)
       return fail(BSMM_E_ARG, "bsmm_updat: no tcgen05 kernel for dtype=%d axis=%d bsize=%d (%s)", dtype, axis, bsize, err_buf());
+    note_fallback("bsmm_updat", dtype);
   }
 
   NtParams p = {};
