@@ -254,7 +254,9 @@ tc_xprop_kernel(const XpropTcParams p, const __grid_constant__ XpropTmaps maps) 
   __shared__ TileQueue tq;
   volatile int* abort_flag = &abort_s;
 
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  // the warp index is made provably warp-uniform (shuffle from lane 0) so that role dispatch, stage indices and descriptor arithmetic
+  // can live in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
   // CL == 2: the queue hands out tile PAIRS (index = minibatch tile * n_ktiles/2 + pair); this CTA takes output tile 2*pair + rank
   const uint32_t crank = CL == 2 ? ptx::cluster_ctarank() : 0u;
   const int kt_per = CL == 2 ? p.n_ktiles / 2 : p.n_ktiles;

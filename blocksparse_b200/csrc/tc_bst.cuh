@@ -47,7 +47,7 @@ tc_bst_nt_kernel(const BstNtParams p, const __grid_constant__ BstNtTmaps maps) {
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   volatile int* abort_flag = &abort_s;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform role index
   const int chunks = p.head_state / 64;
   const long long total = (long long)p.batch * p.heads * p.n_items;
 
@@ -236,7 +236,7 @@ tc_bst_xn_kernel(const BstXnParams p, const __grid_constant__ BstXnTmaps maps) {
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
   volatile int* abort_flag = &abort_s;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform role index
   const int chunks = p.head_state / 64;              // 1 or 2 column atoms of B / D
   const long long total = (long long)p.batch * p.heads * p.n_out;
 

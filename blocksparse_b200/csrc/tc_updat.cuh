@@ -66,7 +66,7 @@ tc_updat_kernel(const UpdatTcParams p, const __grid_constant__ UpdatTmaps maps) 
   __shared__ TileQueue tq;
   volatile int* abort_flag = &abort_s;
 
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform role index
   const int32_t* recs = p.sched + 4;
   const int chunks_per_pair = (p.N + UPDAT_KCHUNK - 1) / UPDAT_KCHUNK;
   const int n_chunks = chunks_per_pair * p.pcount;

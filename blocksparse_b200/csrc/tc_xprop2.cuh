@@ -73,7 +73,7 @@ tc_xprop2_kernel(const Xprop2Params p, const __grid_constant__ XpropTmaps maps) 
   __shared__ int abort_s;
   volatile int* abort_flag = &abort_s;
 
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;   // provably warp-uniform role index
   const int32_t* sched = p.sched;
   const int32_t* tlist = sched + p.list_off;
   const int li0 = tlist[blockIdx.x], li1 = tlist[blockIdx.x + 1];
