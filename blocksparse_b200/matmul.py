@@ -214,14 +214,9 @@ class BlocksparseMatMul(MatmulCheckers):
         n_in, n_out = (self.KB, self.CB) if bprop else (self.CB, self.KB)
         lut = d["bprop" if bprop else "fprop"]
 
-        class _X(object):          # what the schedule selection below reads from the activation tensor
-            pass
-        x = _X()
-        x.dtype, x.device = dtype, device
-        gate = None
         sched, sched_tiles, sched_off = None, 0, 0
         list_off = n_ctas = n_nt = 0
-        variant = self._xprop2_variant(x.dtype, gate) if "xprop_sched" in d else 0
+        variant = self._xprop2_variant(dtype, None) if "xprop_sched" in d else 0
         if variant:
             # pair schedule (csrc/tc_xprop2.cuh): wide activation tiles + host-built per-CTA tile lists
             key = ("pair", bool(bprop), variant, N)
@@ -229,12 +224,12 @@ class BlocksparseMatMul(MatmulCheckers):
             if plan is None:
                 tb, occ, wps = _X2_VARIANTS[variant]
                 n_nt = -(-N // 128)
-                n_ctas = _lib.grid_sms(x.device) * occ
+                n_ctas = _lib.grid_sms(device) * occ
                 n_kt = pick_tile_count(n_out, n_nt, n_ctas, tb)
                 arr, off, loff = self._luts.pair_schedule(bprop, tb, wps, n_kt, n_nt, n_ctas)
                 while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:
                     d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
-                plan = d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), n_kt, off, loff, n_ctas, n_nt, tb | (variant << 8) | (1 << 16))
+                plan = d["xprop_sched"][key] = (torch.as_tensor(arr, device=device), n_kt, off, loff, n_ctas, n_nt, tb | (variant << 8) | (1 << 16))
             sched, sched_tiles, sched_off, list_off, n_ctas, n_nt, tile_arg = plan
         elif "xprop_sched" in d:
             # tile count chosen so that (minibatch tiles) x (feature tiles) fills whole waves of the persistent grid
@@ -251,14 +246,14 @@ class BlocksparseMatMul(MatmulCheckers):
                 # 1..3 W blocks per group on average (density <= 37.5 %): 4 W slots per stage, 6 stages in flight
                 wpg, sparse = 4, True
             n_nt = -(-N // 128)
-            if sparse and self.bsize == 32 and _PAIR_TILES and x.dtype != torch.float32:
+            if sparse and self.bsize == 32 and _PAIR_TILES and dtype != torch.float32:
                 # 2-CTA clusters over neighbouring output tiles sharing every activation tile by TMA multicast (csrc/tc.cuh, CL = 2)
                 key = ("pairtile", bool(bprop), n_kt, wpg)
                 if key not in d["xprop_sched"]:
                     arr, off = self._luts.pair_tile_schedule(bprop, tb, self.bsize, wpg, n_kt)
                     while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:
                         d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
-                    d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off, 0)
+                    d["xprop_sched"][key] = (torch.as_tensor(arr, device=device), int(arr[0]), off, 0)
                 sched, sched_tiles, sched_off, list_off = d["xprop_sched"][key]
                 tile_arg = tb | (wpg << 8) | (1 << 12)
                 key = None
@@ -268,7 +263,7 @@ class BlocksparseMatMul(MatmulCheckers):
                 arr, off, ooff = self._luts.tile_schedule(bprop, tb, self.bsize, wpg, n_tiles=n_kt, n_ntiles=n_nt)
                 while len(d["xprop_sched"]) >= _SCHED_CACHE_MAX:       # bounded: one entry per distinct minibatch tile count
                     d["xprop_sched"].pop(next(iter(d["xprop_sched"])))
-                d["xprop_sched"][key] = (torch.as_tensor(arr, device=x.device), int(arr[0]), off, ooff)
+                d["xprop_sched"][key] = (torch.as_tensor(arr, device=device), int(arr[0]), off, ooff)
             if key is not None:
                 sched, sched_tiles, sched_off, list_off = d["xprop_sched"][key]
                 tile_arg = tb | ((wpg << 8) if sparse else 0)
